@@ -1,0 +1,343 @@
+"""
+tests/golden/make_golden.py — generates the golden fixtures in this directory.
+
+Run ONLY in the build container, where the reference lives at /root/reference:
+    python tests/golden/make_golden.py
+It imports the UNMODIFIED reference (copied to a temp dir only to add the git-ignored
+`_version.py` stub that `pypbr/__init__.py:22` needs), executes it in fp32 (the parity target) and
+fp64 (the arbiter; maps injected through `_maps`, which bypasses the FloatTensor gate of
+`materials/base.py:96-101`), asserts that oracle/pbr_oracle.py is BIT-IDENTICAL to the reference
+on every case (outputs and autograd gradients), and writes one .npz per case.
+
+Nothing at test / bench / smoke time reads /root/reference; they replay these files.
+"""
+
+import json
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+REF_SRC = "/root/reference"
+
+
+def import_reference():
+    tmp = tempfile.mkdtemp(prefix="pypbr_ref_")
+    shutil.copytree(os.path.join(REF_SRC, "pypbr"), os.path.join(tmp, "pypbr"))
+    with open(os.path.join(tmp, "pypbr", "_version.py"), "w") as f:
+        f.write('version = "0.1.0"\n')
+    sys.path.insert(0, tmp)
+    import pypbr  # noqa: F401
+
+    return tmp
+
+
+import_reference()
+from pypbr.blending.functional import blend_materials as ref_blend_materials  # noqa: E402
+from pypbr.io import load_material_from_folder  # noqa: E402
+from pypbr.materials import BasecolorMetallicMaterial, DiffuseSpecularMaterial  # noqa: E402
+from pypbr.models import CookTorranceBRDF  # noqa: E402
+from pypbr.utils import linear_to_srgb as ref_l2s  # noqa: E402
+
+from oracle import pbr_oracle as O  # noqa: E402
+
+
+def bits_equal(a, b):
+    if a is None and b is None:
+        return True
+    a = a.detach().contiguous()
+    b = b.detach().contiguous()
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    return bool(torch.all((a == b) | (torch.isnan(a) & torch.isnan(b))))
+
+
+# ------------------------------------------------------------------------------------------
+# input synthesis
+# ------------------------------------------------------------------------------------------
+
+
+def synth_maps(gen, H, W, workflow, normal="unit", rough_lo=0.2, B=None):
+    shp = (lambda c: (c, H, W)) if B is None else (lambda c: (B, c, H, W))
+    cdim = 0 if B is None else 1
+    maps = {"albedo": torch.rand(shp(3), generator=gen)}
+    if normal == "unit":
+        n = torch.randn(shp(3), generator=gen)
+        scale = torch.tensor([0.3, 0.3, 0.0]).view((3, 1, 1) if B is None else (1, 3, 1, 1))
+        up = torch.tensor([0.0, 0.0, 1.0]).view((3, 1, 1) if B is None else (1, 3, 1, 1))
+        maps["normal"] = torch.nn.functional.normalize(n * scale + up, dim=cdim)
+    elif normal == "raw":  # tests/test_models.py:17,34: un-normalised, any sign
+        maps["normal"] = torch.rand(shp(3), generator=gen) * 2 - 1
+    maps["roughness"] = torch.rand(shp(1), generator=gen) * (1 - rough_lo) + rough_lo
+    if workflow == "metallic":
+        maps["metallic"] = torch.rand(shp(1), generator=gen)
+    else:
+        maps["specular"] = torch.rand(shp(3), generator=gen)
+    return maps
+
+
+def ref_material(maps, dtype, flags, requires_grad=False):
+    cls = BasecolorMetallicMaterial if "metallic" in maps else DiffuseSpecularMaterial
+    m = cls()
+    m.albedo_is_srgb = flags.get("albedo_is_srgb", True)
+    if cls is DiffuseSpecularMaterial:
+        m.specular_is_srgb = flags.get("specular_is_srgb", True)
+    leaves = {}
+    for k, t in maps.items():
+        leaf = t.to(dtype).clone().requires_grad_(requires_grad)
+        leaves[k] = leaf
+        m._maps[k] = leaf
+    if "normal" not in maps:
+        # `material.normal` raises AttributeError unless the key exists (base.py:105-120); the
+        # default +Z branch of cooktorrance.py:143-151 is only reachable with an explicit None entry.
+        m._maps["normal"] = None
+    return m, leaves
+
+
+def ref_render(maps, view, lights, intens, p, dtype, grad_out=None):
+    """Loop of reference calls combined per the module docstring of oracle/pbr_oracle.py."""
+    batched = maps["albedo"].dim() == 4
+    multi = lights.dim() == 2
+    B = maps["albedo"].shape[0] if batched else 1
+    lts = lights if multi else lights.view(1, 3)
+    ins = intens if intens.dim() == 2 else intens.view(1, 3).expand(lts.shape[0], 3)
+    brdf = CookTorranceBRDF(light_type=p["light_type"])
+    leaves_all, outs = [], []
+    for b in range(B):
+        mb = {k: (t[b] if batched else t) for k, t in maps.items()}
+        mat, leaves = ref_material(mb, dtype, p, requires_grad=grad_out is not None)
+        leaves_all.append(leaves)
+        single = (not multi) and True
+        if single:
+            outs.append(brdf(mat, view.to(dtype), lts[0].to(dtype), ins[0].to(dtype), p["light_size"], p["return_srgb"]))
+            continue
+        per = [brdf(mat, view.to(dtype), lts[l].to(dtype), ins[l].to(dtype), p["light_size"], False) for l in range(lts.shape[0])]
+        enc = ref_l2s if p["return_srgb"] else (lambda c: c)
+        if p["accumulate"]:
+            tot = per[0]
+            for q in per[1:]:
+                tot = tot + q
+            outs.append(enc(torch.clamp(tot, 0.0, 1.0)))
+        else:
+            outs.append(torch.stack([enc(q) for q in per], dim=0))
+    out = torch.stack(outs, dim=0) if batched else outs[0]
+    grads = None
+    if grad_out is not None:
+        out.backward(grad_out.to(dtype))
+        grads = {}
+        for k in maps:
+            gs = [lv[k].grad for lv in leaves_all]
+            grads[k] = torch.stack(gs, dim=0) if batched else gs[0]
+    return out.detach(), grads
+
+
+def oracle_render(maps, view, lights, intens, p, dtype, grad_out=None):
+    leaves = {k: t.to(dtype).clone().requires_grad_(grad_out is not None) for k, t in maps.items()}
+    out = O.render(
+        leaves, view.to(dtype), lights.to(dtype), intens.to(dtype), p["light_size"], p["light_type"],
+        p.get("albedo_is_srgb", True), p.get("specular_is_srgb", True), p["return_srgb"], p["accumulate"],
+    )
+    grads = None
+    if grad_out is not None:
+        out.backward(grad_out.to(dtype))
+        grads = {k: leaves[k].grad for k in maps}
+    return out.detach(), grads
+
+
+def ring_lights(L):
+    if L == 1:
+        return torch.tensor([0.1, 0.1, 1.0])
+    ang = torch.arange(L, dtype=torch.float64) * (2 * np.pi / L)
+    return torch.stack([0.4 * torch.cos(ang), 0.4 * torch.sin(ang), torch.ones(L, dtype=torch.float64)], dim=1).float()
+
+
+CT_CASES = [
+    # name, H, W, B, L, params
+    dict(name="ct_metal_point_37x53", H=37, W=53, B=None, L=1, workflow="metallic", normal="unit", rough_lo=0.2,
+         light_type="point", light_size=1.0, return_srgb=True, albedo_is_srgb=True, accumulate=True),
+    dict(name="ct_metal_point_stress_40x64", H=40, W=64, B=None, L=1, workflow="metallic", normal="unit", rough_lo=0.0,
+         light_type="point", light_size=1.0, return_srgb=True, albedo_is_srgb=True, accumulate=True),
+    dict(name="ct_metal_dir_reftest_64x64", H=64, W=64, B=None, L=1, workflow="metallic", normal="raw", rough_lo=0.0,
+         light_type="directional", light_size=None, return_srgb=True, albedo_is_srgb=True, accumulate=True,
+         light=[0.0, 0.0, 1.0]),  # tests/test_models.py:12-27
+    dict(name="ct_spec_point_reftest_64x64", H=64, W=64, B=None, L=1, workflow="specular", normal="raw", rough_lo=0.0,
+         light_type="point", light_size=5.0, return_srgb=True, albedo_is_srgb=True, accumulate=True,
+         light=[0.0, 10.0, 10.0]),  # tests/test_models.py:30-43
+    dict(name="ct_spec_dir_linear_33x47", H=33, W=47, B=None, L=1, workflow="specular", normal="unit", rough_lo=0.2,
+         light_type="directional", light_size=None, return_srgb=False, albedo_is_srgb=False, specular_is_srgb=False,
+         accumulate=True, light=[0.3, -0.2, 0.9], intensity=[2.0, 1.5, 1.0], view=[0.1, 0.2, 1.0]),
+    dict(name="ct_metal_nonormal_32x40", H=32, W=40, B=None, L=1, workflow="metallic", normal=None, rough_lo=0.2,
+         light_type="point", light_size=None, return_srgb=True, albedo_is_srgb=True, accumulate=True,
+         view=[0.2, -0.1, 1.0], intensity=[3.0, 2.5, 2.0]),
+    dict(name="ct_metal_point_B3_L4_acc_24x36", H=24, W=36, B=3, L=4, workflow="metallic", normal="unit", rough_lo=0.2,
+         light_type="point", light_size=1.0, return_srgb=True, albedo_is_srgb=True, accumulate=True),
+    dict(name="ct_metal_point_B2_L3_per_24x36", H=24, W=36, B=2, L=3, workflow="metallic", normal="unit", rough_lo=0.2,
+         light_type="point", light_size=1.0, return_srgb=True, albedo_is_srgb=True, accumulate=False),
+    dict(name="ct_spec_point_B2_L2_acc_20x28", H=20, W=28, B=2, L=2, workflow="specular", normal="unit", rough_lo=0.2,
+         light_type="point", light_size=2.0, return_srgb=True, albedo_is_srgb=True, specular_is_srgb=True, accumulate=True),
+    dict(name="ct_metal_dir_B2_L3_acc_16x20", H=16, W=20, B=2, L=3, workflow="metallic", normal="unit", rough_lo=0.2,
+         light_type="directional", light_size=None, return_srgb=True, albedo_is_srgb=True, accumulate=True),
+]
+
+
+def make_ct_case(idx, c):
+    gen = torch.Generator().manual_seed(1000 + idx)
+    maps = synth_maps(gen, c["H"], c["W"], c["workflow"], c["normal"], c["rough_lo"], c["B"])
+    L = c["L"]
+    lights = torch.tensor(c["light"]) if "light" in c else ring_lights(L)
+    if L > 1:
+        intens = torch.ones(L, 3) * (1.5 / L if c["accumulate"] else 1.0)
+        intens = intens * torch.tensor([1.0, 0.9, 0.8])
+    else:
+        intens = torch.tensor(c.get("intensity", [1.0, 1.0, 1.0]))
+    view = torch.tensor(c.get("view", [0.0, 0.0, 1.0]))
+    p = {k: c.get(k) for k in ("light_type", "light_size", "return_srgb", "albedo_is_srgb", "specular_is_srgb", "accumulate")}
+    p = {k: (True if (v is None and k.endswith("is_srgb")) else v) for k, v in p.items()}
+
+    out32, _ = ref_render(maps, view, lights, intens, p, torch.float32)
+    grad_out = torch.rand(out32.shape, generator=gen)
+    out32, g32 = ref_render(maps, view, lights, intens, p, torch.float32, grad_out)
+    out64, g64 = ref_render(maps, view, lights, intens, p, torch.float64, grad_out)
+    o32, og32 = oracle_render(maps, view, lights, intens, p, torch.float32, grad_out)
+    o64, og64 = oracle_render(maps, view, lights, intens, p, torch.float64, grad_out)
+    assert bits_equal(o32, out32), f"{c['name']}: oracle fp32 forward differs from reference"
+    assert bits_equal(o64, out64), f"{c['name']}: oracle fp64 forward differs from reference"
+    for k in maps:
+        assert bits_equal(og32[k], g32[k]), f"{c['name']}: oracle fp32 grad {k} differs"
+        assert bits_equal(og64[k], g64[k]), f"{c['name']}: oracle fp64 grad {k} differs"
+
+    arrs = {f"in_{k}": v.numpy() for k, v in maps.items()}
+    arrs.update(view=view.numpy(), lights=lights.numpy(), intensity=intens.numpy(), grad_out=grad_out.numpy(),
+                out32=out32.numpy(), out64=out64.numpy().astype(np.float64))
+    for k in maps:
+        arrs[f"g32_{k}"] = g32[k].numpy()
+        arrs[f"g64_{k}"] = g64[k].numpy()
+    arrs["params"] = np.array(json.dumps(p))
+    np.savez_compressed(os.path.join(HERE, c["name"] + ".npz"), **arrs)
+    e = (out32.double() - out64).abs() / out64.abs().clamp_min(1e-6)
+    print(f"{c['name']}: ok  out mean {out32.mean():.6f}  ref32-vs-ref64 max rel {e.max():.2e}")
+
+
+# ------------------------------------------------------------------------------------------
+# workflow conversions, blends
+# ------------------------------------------------------------------------------------------
+
+
+def make_conversion_cases():
+    gen = torch.Generator().manual_seed(77)
+    H, W = 31, 45
+    maps = synth_maps(gen, H, W, "metallic")
+    arrs = {}
+    for srgb in (True, False):
+        m = BasecolorMetallicMaterial(albedo=maps["albedo"], normal=maps["normal"], roughness=maps["roughness"],
+                                      metallic=maps["metallic"], albedo_is_srgb=srgb)
+        d = m.to_diffuse_specular_material()
+        od, os_ = O.metallic_to_specular(maps["albedo"], maps["metallic"], srgb)
+        assert bits_equal(od, d.albedo) and bits_equal(os_, d.specular)
+        assert d.normal is m.normal and d.roughness is m.roughness and d.specular_is_srgb is True and d.albedo_is_srgb is False
+        arrs[f"m2s_diffuse_srgb{int(srgb)}"] = d.albedo.numpy()
+        arrs[f"m2s_specular_srgb{int(srgb)}"] = d.specular.numpy()
+    # edge values through the metallic→specular path
+    smaps = synth_maps(gen, H, W, "specular")
+    # push some texels to the branches of diffuse.py:134-145 (den < eps, m >= 0.95)
+    smaps["albedo"][:, :4] = 0.04
+    smaps["specular"][:, 4:8] = 0.99
+    smaps["albedo"][:, 8:10] = 0.0
+    for srgb in (True, False):
+        m = DiffuseSpecularMaterial(albedo=smaps["albedo"], normal=smaps["normal"], roughness=smaps["roughness"],
+                                    specular=smaps["specular"], albedo_is_srgb=srgb)
+        bm = m.to_basecolor_metallic_material()
+        ob, om = O.specular_to_metallic(smaps["albedo"], smaps["specular"], srgb)
+        assert bits_equal(ob, bm.albedo) and bits_equal(om, bm.metallic)
+        assert bm.metallic.shape[0] == 3
+        arrs[f"s2m_basecolor_srgb{int(srgb)}"] = bm.albedo.numpy()
+        arrs[f"s2m_metallic_srgb{int(srgb)}"] = bm.metallic.numpy()
+    arrs.update({f"in_m_{k}": v.numpy() for k, v in maps.items()})
+    arrs.update({f"in_s_{k}": v.numpy() for k, v in smaps.items()})
+    np.savez_compressed(os.path.join(HERE, "convert_31x45.npz"), **arrs)
+    print("convert_31x45: ok")
+
+
+def make_blend_cases():
+    gen = torch.Generator().manual_seed(99)
+    H, W = 29, 43
+    m1 = synth_maps(gen, H, W, "metallic")
+    m2 = synth_maps(gen, H, W, "metallic", normal="raw")
+    m1["height"] = torch.rand(1, H, W, generator=gen)
+    m2["height"] = torch.rand(1, H, W, generator=gen)
+    m2["opacity"] = torch.rand(1, H, W, generator=gen)  # one-sided map: passed through by reference
+    mask = torch.rand(1, H, W, generator=gen)
+    mats = [BasecolorMetallicMaterial(albedo=m["albedo"], normal=m["normal"], roughness=m["roughness"],
+                                      metallic=m["metallic"], **{k: m[k] for k in ("height", "opacity") if k in m})
+            for m in (m1, m2)]
+    arrs = {f"in1_{k}": v.numpy() for k, v in m1.items()}
+    arrs.update({f"in2_{k}": v.numpy() for k, v in m2.items()})
+    arrs["mask"] = mask.numpy()
+    runs = {
+        "mask": dict(method="mask", mask=mask),
+        "mask2d": dict(method="mask", mask=mask[0]),
+        "height": dict(method="height", blend_width=0.1),
+        "height_w03": dict(method="height", blend_width=0.3),
+        "prop_metallic": dict(method="properties", property_name="metallic", blend_width=0.1),
+        "prop_roughness": dict(method="properties", property_name="roughness", blend_width=0.05),
+        "grad_h": dict(method="gradient", direction="horizontal"),
+        "grad_v": dict(method="gradient", direction="vertical"),
+    }
+    for tag, kw in runs.items():
+        blended, used_mask = ref_blend_materials(mats[0], mats[1], **kw)
+        # oracle: mask builders + map arithmetic + the setattr normal re-ingestion quirk
+        if kw["method"] == "mask":
+            om = kw["mask"]
+        elif kw["method"] == "height":
+            om = O.sigmoid_mask(m1["height"], m2["height"], kw["blend_width"])
+        elif kw["method"] == "properties":
+            om = O.property_mask(m1[kw["property_name"]], m2[kw["property_name"]], kw["blend_width"])
+        else:
+            om = O.gradient_mask(H, W, kw["direction"])
+        ob = O.blend_maps(m1, m2, om)
+        ob["normal"] = O.process_normal_map(ob["normal"])
+        om3 = om.unsqueeze(0) if om.dim() == 2 else om
+        assert bits_equal(om3, used_mask), tag
+        for k, v in blended._maps.items():
+            assert bits_equal(ob[k], v), (tag, k)
+            arrs[f"{tag}_{k}"] = v.numpy()
+        arrs[f"{tag}_mask"] = used_mask.numpy()
+    np.savez_compressed(os.path.join(HERE, "blend_29x43.npz"), **arrs)
+    print("blend_29x43: ok")
+
+
+def make_config1_fixture():
+    """BASELINE.json configs[0]: tiles fixture, metallic workflow, 256x256, example lighting."""
+    mat = load_material_from_folder(os.path.join(REF_SRC, "tests", "data", "tiles"), preferred_workflow="metallic")
+    mat.resize((256, 256))
+    brdf = CookTorranceBRDF(light_type="point")
+    view = torch.tensor([0.0, 0.0, 1.0])
+    light = torch.tensor([0.1, 0.1, 1.0])
+    inten = torch.tensor([1.0, 1.0, 1.0])
+    out = brdf(mat, view, light, inten, 1.0)
+    names = [k for k in ("albedo", "normal", "roughness", "metallic") if mat._maps.get(k) is not None]
+    maps = {k: mat._maps[k] for k in names}
+    p = dict(light_type="point", light_size=1.0, return_srgb=True, albedo_is_srgb=mat.albedo_is_srgb, accumulate=True)
+    o32, _ = oracle_render(maps, view, light, inten, p, torch.float32)
+    assert bits_equal(o32, out)
+    arrs = {f"in_{k}": v.numpy() for k, v in maps.items()}
+    arrs.update(view=view.numpy(), lights=light.numpy(), intensity=inten.numpy(), out32=out.numpy(),
+                params=np.array(json.dumps(p)))
+    np.savez_compressed(os.path.join(HERE, "config1_tiles_256.npz"), **arrs)
+    print(f"config1_tiles_256: ok  mean {out.mean():.7f} min {out.min():.5f} max {out.max():.5f}")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    for i, c in enumerate(CT_CASES):
+        make_ct_case(i, c)
+    make_conversion_cases()
+    make_blend_cases()
+    make_config1_fixture()
