@@ -1,0 +1,188 @@
+/*
+ * pbrcuda.h — C ABI of libpbrcuda.so: the B200 (sm_100a) per-texel shading hot path of PyPBR.
+ *
+ * The reference (giuvecchio/PyPBR, pure Python) has no FFI layer: its boundary for this path is the
+ * Python API.  Every entry point below replaces the ATen eager-op sequence inside one reference
+ * function; the Python host layer (pypbr_b200/) keeps the reference's names and signatures and calls
+ * these through ctypes (INTEGRATION.md shows the stub a PyPBR maintainer would add).
+ *
+ * Conventions
+ *   - every function returns int: 0 = OK, negative = PBR_E_* (argument errors, detected on the host
+ *     before any launch), positive = cudaError_t of the launch.  Nothing throws, nothing allocates
+ *     device memory, nothing synchronises: work is enqueued on `stream` of the CURRENT device.
+ *   - all maps are float32, channel-planar, with unit stride along W; batch / channel / row strides
+ *     are given in ELEMENTS (so crops and batched (B,C,H,W) or unbatched (C,H,W) tensors are passed
+ *     without a copy).  128-bit vector access is used when every pointer is 16-byte aligned and every
+ *     stride is a multiple of 4; otherwise the same kernels run their scalar path.
+ *   - the caller owns every buffer and keeps it alive until the stream has passed the launch.
+ *   - the library keeps no mutable global state except an atomic launch counter; it is re-entrant
+ *     and thread-safe.
+ */
+#ifndef PBRCUDA_H_
+#define PBRCUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBR_ABI_VERSION 1
+#define PBR_MAX_LIGHTS 64      /* lights per launch (parameters are staged in shared memory) */
+#define PBR_MAX_BLEND_MAPS 12  /* maps blended by one pbr_blend launch */
+
+/* error codes (negative) */
+#define PBR_OK 0
+#define PBR_E_NULL (-1)        /* required pointer is NULL */
+#define PBR_E_SHAPE (-2)       /* B/H/W/L out of range */
+#define PBR_E_ENUM (-3)        /* workflow / light_type / mode out of range */
+#define PBR_E_TOO_MANY (-4)    /* L > PBR_MAX_LIGHTS or n_maps > PBR_MAX_BLEND_MAPS */
+#define PBR_E_CHANNELS (-5)    /* unsupported channel count */
+
+typedef void* pbr_stream_t;    /* cudaStream_t */
+
+/* One channel-planar map: element (b, c, y, x) lives at ptr[b*sb + c*sc + y*sh + x]. */
+typedef struct PbrPlane {
+  float* ptr;
+  int64_t sb, sc, sh;
+} PbrPlane;
+
+enum { PBR_WORKFLOW_METALLIC = 0, PBR_WORKFLOW_SPECULAR = 1 };
+enum { PBR_LIGHT_DIRECTIONAL = 0, PBR_LIGHT_POINT = 1 };
+
+/*
+ * Cook-Torrance shading descriptor.
+ * Replaces CookTorranceBRDF.forward, pypbr/models/cooktorrance.py:68-182 (with fresnel_schlick
+ * :184-196, normal_distribution_ggx :198-218, geometry_schlick_ggx :220-235, geometry_smith :237-260),
+ * MaterialBase.linear_albedo pypbr/materials/base.py:262-277, DiffuseSpecularMaterial.linear_specular
+ * pypbr/materials/diffuse.py:76-91, srgb_to_linear / linear_to_srgb pypbr/utils/functions.py:31-66.
+ */
+typedef struct PbrCtDesc {
+  int32_t B, H, W, L;
+  int32_t workflow;         /* PBR_WORKFLOW_*  (cooktorrance.py:103-118) */
+  int32_t light_type;       /* PBR_LIGHT_*     (cooktorrance.py:125-142) */
+  int32_t albedo_is_srgb;   /* base.py:272 */
+  int32_t specular_is_srgb; /* diffuse.py:86 */
+  int32_t return_srgb;      /* cooktorrance.py:179 */
+  int32_t per_light;        /* 0: accumulate L lights into (B,3,H,W); 1: write (B,L,3,H,W) */
+  int32_t params_on_device; /* 0: view/lights/intensity are HOST arrays (copied into the launch); 1: device arrays */
+  float light_size;         /* physical plane size for point lights; <= 0 means 1.0 (cooktorrance.py:130) */
+  PbrPlane albedo;          /* 3 ch */
+  PbrPlane normal;          /* 3 ch, already in [-1,1]; ptr == NULL -> (0,0,1) (cooktorrance.py:143-151) */
+  PbrPlane roughness;       /* 1 ch */
+  PbrPlane metspec;         /* metallic: 1 ch (or 3, see metallic_channels); specular: 3 ch */
+  int32_t metallic_channels;/* metallic workflow: 1 (usual) or 3 (the per-channel metallic that
+                               to_basecolor_metallic_material produces, diffuse.py:150-156); 0 means 1 */
+  const float* view;        /* 3 floats, not normalised */
+  const float* lights;      /* L*3: direction (directional) or position (point) */
+  const float* intensity;   /* L*3 */
+  PbrPlane out;             /* 3 ch; per_light: sb is the stride of b, `out_sl` the stride of l */
+  int64_t out_sl;
+} PbrCtDesc;
+
+/* Gradient buffers for pbr_ct_backward.  Any d_* with ptr == NULL is not computed. */
+typedef struct PbrCtGrads {
+  PbrPlane grad_out;        /* same logical shape as PbrCtDesc.out */
+  int64_t grad_out_sl;
+  PbrPlane d_albedo;        /* 3 ch */
+  PbrPlane d_normal;        /* 3 ch */
+  PbrPlane d_roughness;     /* 1 ch */
+  PbrPlane d_metspec;       /* 1 or 3 ch */
+  float* d_intensity;       /* device, L*3, ACCUMULATED with atomics: caller zero-fills; may be NULL */
+} PbrCtGrads;
+
+/*
+ * Fused rendering-loss step (docs/source/tutorials/06_advanced.rst:73-107 scaled to a batch):
+ *   loss_sum += sum((render(desc) - target)^2)   over every element this launch covers,
+ *   d_* = d(loss_scale * that sum)/d(map), where the caller passes loss_scale = 1/numel for MSE.
+ * The colour image is never written.  Per-tile warp-shuffle reduction, one atomic per CTA.
+ */
+typedef struct PbrCtLoss {
+  PbrPlane target;          /* same logical shape as the render (desc.out is ignored) */
+  int64_t target_sl;
+  float loss_scale;
+  float* loss_sum;          /* device scalar, ACCUMULATED: caller zero-fills */
+} PbrCtLoss;
+
+/*
+ * Workflow conversions.
+ * m2s replaces BasecolorMetallicMaterial.to_diffuse_specular_material arithmetic, pypbr/materials/metallic.py:90-109.
+ * s2m replaces DiffuseSpecularMaterial.to_basecolor_metallic_material arithmetic, pypbr/materials/diffuse.py:112-147.
+ */
+typedef struct PbrConvDesc {
+  int32_t B, H, W;
+  int32_t albedo_is_srgb;
+  PbrPlane albedo;          /* in, 3 ch */
+  PbrPlane metspec;         /* in: metallic 1 ch (m2s) / raw specular 3 ch (s2m) */
+  PbrPlane out0;            /* out 3 ch: diffuse (m2s) / basecolor (s2m) */
+  PbrPlane out1;            /* out 3 ch: specular (m2s) / metallic, 3 channels (s2m) */
+} PbrConvDesc;
+
+/*
+ * Blending.  Replaces blend_with_mask / _blend_normals / blend_on_height / blend_on_properties /
+ * blend_with_gradient arithmetic, pypbr/blending/functional.py:64-286: mask construction, the per-map
+ * lerp `mask*m1 + (1-mask)*m2`, and the normalise-lerp-normalise of normal maps, all maps in one pass.
+ */
+enum { PBR_MASK_GIVEN = 0, PBR_MASK_SIGMOID = 1, PBR_MASK_GRADIENT_H = 2, PBR_MASK_GRADIENT_V = 3 };
+
+typedef struct PbrBlendMap {
+  PbrPlane a, b, out;
+  int32_t channels;         /* 1..4 */
+  int32_t is_normal;        /* 1: _blend_normals (functional.py:119-145), requires channels == 3 */
+} PbrBlendMap;
+
+typedef struct PbrBlendDesc {
+  int32_t B, H, W;
+  int32_t n_maps;
+  int32_t mask_mode;        /* PBR_MASK_* */
+  float blend_width;        /* sigmoid: mask = sigmoid(((p1 + shift) - p2) / (blend_width + 1e-6)) */
+  float shift;
+  int32_t apply_shift;      /* blend_on_height adds `shift` (functional.py:188); blend_on_properties has no such op */
+  PbrPlane mask;            /* GIVEN: input (1 ch; sb may be 0 to broadcast over the batch) */
+  PbrPlane prop1, prop2;    /* SIGMOID: the two 1-ch property / height maps */
+  PbrPlane mask_out;        /* non-GIVEN modes: the mask is returned to the caller, so it is written (1 ch); may be NULL */
+  float* normal_min;        /* optional device scalar (caller sets +inf): min over the blended normal, the
+                               `normal_map.min() < 0` probe of MaterialBase._process_normal_map base.py:212 */
+  PbrBlendMap maps[PBR_MAX_BLEND_MAPS];
+} PbrBlendDesc;
+
+/* sRGB <-> linear on an arbitrary C-channel map (pypbr/utils/functions.py:31-66). to_linear: 1 = decode, 0 = encode. */
+typedef struct PbrColorDesc {
+  int32_t B, C, H, W;
+  int32_t to_linear;
+  PbrPlane in, out;
+} PbrColorDesc;
+
+/*
+ * Normal-map ingestion (MaterialBase._process_normal_map, pypbr/materials/base.py:191-242).
+ * pbr_normal_min: *result = min(*result, min over all elements)  (the `min() < 0` probe, base.py:212).
+ * pbr_normal_ingest: channels == 3: normalize(n*2-1) (base.py:215-217);
+ *                    channels == 2: xy*2-1, z = sqrt(clamp(1-x^2-y^2, 1e-6)), normalise (base.py:223-242).
+ */
+typedef struct PbrNormalDesc {
+  int32_t B, H, W;
+  int32_t channels;         /* of `in`: 2 or 3; `out` always has 3 */
+  PbrPlane in, out;
+} PbrNormalDesc;
+
+int pbr_abi_version(void);
+const char* pbr_strerror(int code);
+
+int pbr_ct_forward(const PbrCtDesc* desc, pbr_stream_t stream);
+int pbr_ct_backward(const PbrCtDesc* desc, const PbrCtGrads* grads, pbr_stream_t stream);
+int pbr_ct_loss_fwd_bwd(const PbrCtDesc* desc, const PbrCtLoss* loss, const PbrCtGrads* grads, pbr_stream_t stream);
+
+int pbr_convert_m2s(const PbrConvDesc* desc, pbr_stream_t stream);
+int pbr_convert_s2m(const PbrConvDesc* desc, pbr_stream_t stream);
+int pbr_blend(const PbrBlendDesc* desc, pbr_stream_t stream);
+int pbr_color_convert(const PbrColorDesc* desc, pbr_stream_t stream);
+int pbr_normal_min(const PbrNormalDesc* desc, float* result, pbr_stream_t stream);
+int pbr_normal_ingest(const PbrNormalDesc* desc, pbr_stream_t stream);
+
+/* Number of kernel launches this process has enqueued through the library (for bench accounting). */
+uint64_t pbr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBRCUDA_H_ */

@@ -1,0 +1,185 @@
+"""
+pypbr_b200._cabi — ctypes binding of libpbrcuda.so (include/pbrcuda.h).
+
+This is the only place the package touches native code.  There is NO fallback: if the shared library
+is missing or a tensor is not a CUDA float32 tensor, the call raises.  PyTorch is used for device
+memory, streams and autograd plumbing only; every per-texel operation of the hot path runs in the
+kernels behind these entry points.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
+from typing import Optional, Sequence
+
+import torch
+
+PBR_MAX_LIGHTS = 64
+PBR_MAX_BLEND_MAPS = 12
+
+WORKFLOW_METALLIC, WORKFLOW_SPECULAR = 0, 1
+LIGHT_DIRECTIONAL, LIGHT_POINT = 0, 1
+MASK_GIVEN, MASK_SIGMOID, MASK_GRADIENT_H, MASK_GRADIENT_V = 0, 1, 2, 3
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libpbrcuda.so")
+
+
+class PbrPlane(Structure):
+    _fields_ = [("ptr", c_void_p), ("sb", c_int64), ("sc", c_int64), ("sh", c_int64)]
+
+
+class PbrCtDesc(Structure):
+    _fields_ = [
+        ("B", c_int32), ("H", c_int32), ("W", c_int32), ("L", c_int32),
+        ("workflow", c_int32), ("light_type", c_int32),
+        ("albedo_is_srgb", c_int32), ("specular_is_srgb", c_int32), ("return_srgb", c_int32),
+        ("per_light", c_int32), ("params_on_device", c_int32),
+        ("light_size", c_float),
+        ("albedo", PbrPlane), ("normal", PbrPlane), ("roughness", PbrPlane), ("metspec", PbrPlane),
+        ("metallic_channels", c_int32),
+        ("view", c_void_p), ("lights", c_void_p), ("intensity", c_void_p),
+        ("out", PbrPlane), ("out_sl", c_int64),
+    ]
+
+
+class PbrCtGrads(Structure):
+    _fields_ = [
+        ("grad_out", PbrPlane), ("grad_out_sl", c_int64),
+        ("d_albedo", PbrPlane), ("d_normal", PbrPlane), ("d_roughness", PbrPlane), ("d_metspec", PbrPlane),
+        ("d_intensity", c_void_p),
+    ]
+
+
+class PbrCtLoss(Structure):
+    _fields_ = [("target", PbrPlane), ("target_sl", c_int64), ("loss_scale", c_float), ("loss_sum", c_void_p)]
+
+
+class PbrConvDesc(Structure):
+    _fields_ = [
+        ("B", c_int32), ("H", c_int32), ("W", c_int32), ("albedo_is_srgb", c_int32),
+        ("albedo", PbrPlane), ("metspec", PbrPlane), ("out0", PbrPlane), ("out1", PbrPlane),
+    ]
+
+
+class PbrBlendMap(Structure):
+    _fields_ = [("a", PbrPlane), ("b", PbrPlane), ("out", PbrPlane), ("channels", c_int32), ("is_normal", c_int32)]
+
+
+class PbrBlendDesc(Structure):
+    _fields_ = [
+        ("B", c_int32), ("H", c_int32), ("W", c_int32), ("n_maps", c_int32), ("mask_mode", c_int32),
+        ("blend_width", c_float), ("shift", c_float), ("apply_shift", c_int32),
+        ("mask", PbrPlane), ("prop1", PbrPlane), ("prop2", PbrPlane), ("mask_out", PbrPlane),
+        ("normal_min", c_void_p),
+        ("maps", PbrBlendMap * PBR_MAX_BLEND_MAPS),
+    ]
+
+
+class PbrColorDesc(Structure):
+    _fields_ = [
+        ("B", c_int32), ("C", c_int32), ("H", c_int32), ("W", c_int32), ("to_linear", c_int32),
+        ("in_", PbrPlane), ("out", PbrPlane),
+    ]
+
+
+class PbrNormalDesc(Structure):
+    _fields_ = [("B", c_int32), ("H", c_int32), ("W", c_int32), ("channels", c_int32), ("in_", PbrPlane), ("out", PbrPlane)]
+
+
+_lib = None
+
+# every symbol include/pbrcuda.h declares (tests check that the built library exports all of them)
+EXPORTS = (
+    "pbr_abi_version", "pbr_strerror", "pbr_ct_forward", "pbr_ct_backward", "pbr_ct_loss_fwd_bwd",
+    "pbr_convert_m2s", "pbr_convert_s2m", "pbr_blend", "pbr_color_convert", "pbr_normal_min",
+    "pbr_normal_ingest", "pbr_launch_count",
+)
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load libpbrcuda.so (once).  Raises ImportError if it was not built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"pypbr_b200: native library not found at {_LIB_PATH}. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+            "There is no CPU or PyTorch fallback for the shading path."
+        )
+    lib = ctypes.CDLL(_LIB_PATH)
+    lib.pbr_abi_version.restype = c_int
+    lib.pbr_strerror.restype = c_char_p
+    lib.pbr_strerror.argtypes = [c_int]
+    lib.pbr_launch_count.restype = c_uint64
+    lib.pbr_ct_forward.argtypes = [POINTER(PbrCtDesc), c_void_p]
+    lib.pbr_ct_backward.argtypes = [POINTER(PbrCtDesc), POINTER(PbrCtGrads), c_void_p]
+    lib.pbr_ct_loss_fwd_bwd.argtypes = [POINTER(PbrCtDesc), POINTER(PbrCtLoss), POINTER(PbrCtGrads), c_void_p]
+    lib.pbr_convert_m2s.argtypes = [POINTER(PbrConvDesc), c_void_p]
+    lib.pbr_convert_s2m.argtypes = [POINTER(PbrConvDesc), c_void_p]
+    lib.pbr_blend.argtypes = [POINTER(PbrBlendDesc), c_void_p]
+    lib.pbr_color_convert.argtypes = [POINTER(PbrColorDesc), c_void_p]
+    lib.pbr_normal_min.argtypes = [POINTER(PbrNormalDesc), c_void_p, c_void_p]
+    lib.pbr_normal_ingest.argtypes = [POINTER(PbrNormalDesc), c_void_p]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("pbr_strerror", "pbr_launch_count"):
+            fn.restype = c_int
+    if lib.pbr_abi_version() != 1:
+        raise ImportError(f"pypbr_b200: ABI version mismatch in {_LIB_PATH}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().pbr_strerror(rc).decode()
+        raise RuntimeError(f"pypbr_b200: {what} failed: {msg} (code {rc})")
+
+
+def launch_count() -> int:
+    return int(load().pbr_launch_count())
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"pypbr_b200: {name} lives on {t.device}; the shading path runs on CUDA only (no CPU fallback). "
+            "Move the material with material.to('cuda') or construct CookTorranceBRDF(override_device='cuda')."
+        )
+    if t.dtype != torch.float32:
+        raise TypeError(f"pypbr_b200: {name} must be float32, got {t.dtype}")
+
+
+def rowmajor(t: torch.Tensor) -> torch.Tensor:
+    """The kernels need unit stride along W; everything else is expressed through strides."""
+    return t if (t.stride(-1) == 1 or t.shape[-1] == 1) else t.contiguous()
+
+
+def plane(t: Optional[torch.Tensor]) -> PbrPlane:
+    """(C,H,W) or (B,C,H,W) tensor -> PbrPlane (strides in elements).  None -> NULL plane."""
+    if t is None:
+        return PbrPlane(None, 0, 0, 0)
+    assert t.stride(-1) == 1 or t.shape[-1] == 1, "call rowmajor() first"
+    if t.dim() == 3:
+        return PbrPlane(t.data_ptr(), 0, t.stride(0), t.stride(1))
+    if t.dim() == 4:
+        return PbrPlane(t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
+    raise ValueError(f"maps must be (C,H,W) or (B,C,H,W), got shape {tuple(t.shape)}")
+
+
+def stream_ptr(device: torch.device) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def host_floats(values: Sequence[float]):
+    arr = (c_float * len(values))(*values)
+    return arr

@@ -1,0 +1,807 @@
+// pbr_kernels.cu — sm_100a kernels and the C ABI of libpbrcuda.so (include/pbrcuda.h).
+//
+// Thread mapping shared by every kernel: one thread owns kTexels consecutive texels of one row
+// (128-bit LDG/STG per plane when the layout allows it), a CTA covers blockDim.y rows x
+// blockDim.x*kTexels columns, blockIdx.z is the material of the batch.  All maps are channel-planar,
+// so every warp-level load is a run of 512 contiguous bytes of one plane.
+//
+// The view / light parameters are staged once per CTA in shared memory by the prologue
+// (normalised view vector, per-light position + intensity, and for directional lights the complete,
+// image-constant light geometry), then broadcast-read inside the light loop.
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+#include "../../include/pbrcuda.h"
+#include "pbr_shade.cuh"
+
+namespace pbr {
+
+constexpr int kTexels = 4;      // texels per thread (one float4 per plane)
+constexpr int kThreads = 256;   // threads per CTA
+
+static std::atomic<uint64_t> g_launches{0};
+
+// ------------------------------------------------------------------------------------------------
+// row-segment load / store (streaming: every byte is touched once -> evict-first cache hints)
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void load_seg(const float* __restrict__ p, bool vec, int valid, float (&dst)[N]) {
+  if (N == 4 && vec) {
+    float4 v = __ldcs(reinterpret_cast<const float4*>(p));
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+  } else if (N == 2 && vec) {
+    float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+    dst[0] = v.x; dst[1] = v.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) dst[i] = __ldcs(p + (i < valid ? i : (valid > 0 ? valid - 1 : 0)));
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void store_seg(float* __restrict__ p, bool vec, int valid, const float (&src)[N]) {
+  if (N == 4 && vec) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(src[0], src[1], src[2], src[3]));
+  } else if (N == 2 && vec) {
+    __stcs(reinterpret_cast<float2*>(p), make_float2(src[0], src[1]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (i < valid) __stcs(p + i, src[i]);
+  }
+}
+
+__device__ __forceinline__ int64_t plane_off(const PbrPlane& pl, int b, int c, int row, int col) {
+  return (int64_t)b * pl.sb + (int64_t)c * pl.sc + (int64_t)row * pl.sh + col;
+}
+
+// position of this thread's texel group; out-of-range threads are clamped onto the last valid group
+// (so warp-wide reductions stay convergent) and flagged inactive.
+struct Where {
+  int b, row, col0, valid;
+  bool active, vec;
+};
+__device__ __forceinline__ Where locate(int H, int W, bool vec_ok) {
+  Where w;
+  w.b = blockIdx.z;
+  int row = blockIdx.y * blockDim.y + threadIdx.y;
+  int col0 = (blockIdx.x * blockDim.x + threadIdx.x) * kTexels;
+  w.active = row < H && col0 < W;
+  w.row = row < H ? row : H - 1;
+  w.col0 = col0 < W ? col0 : ((W - 1) / kTexels) * kTexels;
+  int rem = W - w.col0;
+  w.valid = rem < kTexels ? rem : kTexels;
+  w.vec = vec_ok && w.valid == kTexels;
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cook-Torrance kernels
+// ------------------------------------------------------------------------------------------------
+#ifndef PBR_FWD_GROUP
+#define PBR_FWD_GROUP 4   // texels shaded together (ILP) by the forward kernel: 1, 2 or 4
+#endif
+#ifndef PBR_BWD_GROUP
+#define PBR_BWD_GROUP 2   // ... by the backward kernel (register pressure: 2)
+#endif
+
+struct CtKParams {
+  int B, H, W;
+  int mats_per_cta;      // materials a thread walks over (blockIdx.z selects the chunk)
+  CtFlags flags;
+  int vec_ok;
+  int is_loss;           // backward: grad_out is derived from (render - target)
+  PbrPlane albedo, normal, roughness, metspec, out;
+  int64_t out_sl;
+  // backward: `gsrc` is grad_out, or the target image when is_loss
+  PbrPlane gsrc;
+  int64_t gsrc_sl;
+  PbrPlane d_albedo, d_normal, d_roughness, d_metspec;
+  float* d_intensity;
+  float loss_scale;
+  float* loss_sum;
+  // staging sources
+  Linspace lsx, lsy;
+  const float* view_dev;    // non-null: parameters live in device memory
+  const float* lights_dev;
+  const float* inten_dev;
+  float view[3];
+  float lights[PBR_MAX_LIGHTS * 3];
+  float inten[PBR_MAX_LIGHTS * 3];
+};
+
+__device__ __forceinline__ void stage_params(const CtKParams& p, CtStage& S) {
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nth = blockDim.x * blockDim.y;
+  const float* view = p.view_dev ? p.view_dev : p.view;
+  const float* lights = p.lights_dev ? p.lights_dev : p.lights;
+  const float* inten = p.inten_dev ? p.inten_dev : p.inten;
+  if (tid < p.flags.L || tid == 0) {
+    float vx, vy, vz;
+    stage_view(view, vx, vy, vz);
+    if (tid == 0) {
+      S.vx = vx; S.vy = vy; S.vz = vz;
+      S.lsx = p.lsx; S.lsy = p.lsy;
+    }
+    for (int l = tid; l < p.flags.L; l += nth) stage_light(l, lights, inten, p.flags.point, vx, vy, vz, S.light[l]);
+  }
+  __syncthreads();
+}
+
+template <int WF>
+__device__ __forceinline__ void load_material(const CtKParams& p, const Where& w, int b, float (&araw)[3][kTexels],
+                                              float (&nraw)[3][kTexels], float (&rough)[kTexels],
+                                              float (&mraw)[3][kTexels]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) load_seg<kTexels>(p.albedo.ptr + plane_off(p.albedo, b, c, w.row, w.col0), w.vec, w.valid, araw[c]);
+  if (p.normal.ptr) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) load_seg<kTexels>(p.normal.ptr + plane_off(p.normal, b, c, w.row, w.col0), w.vec, w.valid, nraw[c]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i) { nraw[0][i] = 0.0f; nraw[1][i] = 0.0f; nraw[2][i] = 1.0f; }
+  }
+  load_seg<kTexels>(p.roughness.ptr + plane_off(p.roughness, b, 0, w.row, w.col0), w.vec, w.valid, rough);
+  constexpr int mc = WF == 0 ? 1 : 3;  // WF: 0 metallic (1 ch), 1 specular, 2 metallic (3 ch)
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (c < mc) {
+      load_seg<kTexels>(p.metspec.ptr + plane_off(p.metspec, b, c, w.row, w.col0), w.vec, w.valid, mraw[c]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kTexels; ++i) mraw[c][i] = 0.0f;
+    }
+  }
+}
+
+template <int kLight>
+__device__ __forceinline__ void grid_coords(const CtStage& S, const Where& w, float (&x)[kTexels], float& y,
+                                            LightGeom (&hg)[kTexels]) {
+#pragma unroll
+  for (int i = 0; i < kTexels; ++i) {
+    int col = w.col0 + i;
+    x[i] = linspace_at(S.lsx, col < S.lsx.n ? col : S.lsx.n - 1);
+  }
+  y = linspace_at(S.lsy, w.row);
+  if (kLight == kLightPointHoisted) {
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i)
+      point_light_geom(S.light[0].p[0], S.light[0].p[1], S.light[0].p[2], x[i], y, S.vx, S.vy, S.vz, hg[i]);
+  }
+}
+
+template <int G, int N>
+__device__ __forceinline__ void slice3(const float (&src)[3][N], int s, float (&dst)[3][G]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int i = 0; i < G; ++i) dst[c][i] = src[c][s + i];
+}
+
+template <int WF, int kLight>
+__global__ void __launch_bounds__(kThreads) ct_forward_kernel(const __grid_constant__ CtKParams p) {
+  constexpr int G = PBR_FWD_GROUP;
+  __shared__ CtStage S;
+  stage_params(p, S);
+  const Where w = locate(p.H, p.W, p.vec_ok != 0);
+  if (!w.active) return;
+
+  float x[kTexels], y;
+  LightGeom hg[kTexels];
+  grid_coords<kLight>(S, w, x, y, hg);
+
+  const int b0 = blockIdx.z * p.mats_per_cta;
+  const int b1 = min(b0 + p.mats_per_cta, p.B);
+  for (int b = b0; b < b1; ++b) {
+    float araw[3][kTexels], nraw[3][kTexels], rough[kTexels], mraw[3][kTexels];
+    load_material<WF>(p, w, b, araw, nraw, rough, mraw);
+    float outv[3][kTexels];
+#pragma unroll
+    for (int s = 0; s < kTexels; s += G) {
+      float a[3][G], n[3][G], r[G], m[3][G], xs[G];
+      LightGeom hgs[G];
+      slice3<G>(araw, s, a); slice3<G>(nraw, s, n); slice3<G>(mraw, s, m);
+#pragma unroll
+      for (int i = 0; i < G; ++i) { r[i] = rough[s + i]; xs[i] = x[s + i]; hgs[i] = hg[s + i]; }
+      auto emit = [&](int l, const float(&v)[3][G]) {
+        if (p.flags.per_light) {
+          // one image per light: store this sub-group directly (64/128-bit when the group allows)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            int vs = w.valid - s;
+            store_seg<G>(p.out.ptr + plane_off(p.out, b, c, w.row, w.col0 + s) + (int64_t)l * p.out_sl, w.vec,
+                         vs < 0 ? 0 : vs, v[c]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int i = 0; i < G; ++i) outv[c][s + i] = v[c][i];
+        }
+      };
+      ct_forward_group<WF, kLight, G>(S, p.flags, a, n, r, m, xs, y, hgs, emit);
+    }
+    if (!p.flags.per_light) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        store_seg<kTexels>(p.out.ptr + plane_off(p.out, b, c, w.row, w.col0), w.vec, w.valid, outv[c]);
+    }
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Backward / fused loss.  Runtime (warp-uniform) switches:
+//   p.is_loss     : gsrc is the target image; grad_out = 2*loss_scale*(render - target) and the squared
+//                   error is reduced warp-shuffle -> shared -> ONE atomic per CTA.
+//   p.d_intensity : per-light intensity gradients, reduced the same way.
+template <int WF, int kLight>
+__global__ void __launch_bounds__(kThreads) ct_backward_kernel(const __grid_constant__ CtKParams p) {
+  constexpr int G = PBR_BWD_GROUP;
+  __shared__ CtStage S;
+  __shared__ float s_int[PBR_MAX_LIGHTS * 3];
+  __shared__ float s_loss[kThreads / 32];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const bool int_grad = p.d_intensity != nullptr;
+  const bool is_loss = p.is_loss != 0;
+  if (int_grad) {
+    for (int i = tid; i < p.flags.L * 3; i += kThreads) s_int[i] = 0.0f;
+  }
+  stage_params(p, S);  // ends with __syncthreads()
+  const Where w = locate(p.H, p.W, p.vec_ok != 0);
+  const float live = w.active ? 1.0f : 0.0f;
+  if (!w.active && !int_grad && !is_loss) return;  // nothing to reduce: edge threads may leave
+
+  float x[kTexels], y;
+  LightGeom hg[kTexels];
+  grid_coords<kLight>(S, w, x, y, hg);
+
+  float loss_local = 0.0f;
+  const int b0 = blockIdx.z * p.mats_per_cta;
+  const int b1 = min(b0 + p.mats_per_cta, p.B);
+  for (int b = b0; b < b1; ++b) {
+    float araw[3][kTexels], nraw[3][kTexels], rough[kTexels], mraw[3][kTexels];
+    load_material<WF>(p, w, b, araw, nraw, rough, mraw);
+    float d_albedo[3][kTexels], d_normal[3][kTexels], d_rough[kTexels], d_met[3][kTexels];
+#pragma unroll
+    for (int s = 0; s < kTexels; s += G) {
+      float a[3][G], n[3][G], r[G], m[3][G], xs[G];
+      LightGeom hgs[G];
+      slice3<G>(araw, s, a); slice3<G>(nraw, s, n); slice3<G>(mraw, s, m);
+#pragma unroll
+      for (int i = 0; i < G; ++i) { r[i] = rough[s + i]; xs[i] = x[s + i]; hgs[i] = hg[s + i]; }
+      const int vs = (w.valid - s) < 0 ? 0 : (w.valid - s);
+      auto gout = [&](int l, const float(&outv)[3][G], float(&g)[3][G]) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float tv[G];
+          load_seg<G>(p.gsrc.ptr + plane_off(p.gsrc, b, c, w.row, w.col0 + s) + (int64_t)l * p.gsrc_sl, w.vec, vs, tv);
+#pragma unroll
+          for (int i = 0; i < G; ++i) {
+            if (is_loss) {
+              float diff = (i < vs) ? outv[c][i] - tv[i] : 0.0f;
+              loss_local += diff * diff;
+              g[c][i] = 2.0f * p.loss_scale * diff;
+            } else {
+              g[c][i] = (i < vs) ? tv[i] : 0.0f;
+            }
+          }
+        }
+      };
+      auto int_sink = [&](int l, const float(&gi)[3]) {
+        if (int_grad) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float sum = warp_sum(gi[c] * live);
+            if ((tid & 31) == 0) atomicAdd(&s_int[3 * l + c], sum);
+          }
+        }
+      };
+      float da[3][G], dn[3][G], dr[G], dm[3][G];
+      ct_backward_group<WF, kLight, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm);
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { d_albedo[c][s + i] = da[c][i]; d_normal[c][s + i] = dn[c][i]; d_met[c][s + i] = dm[c][i]; }
+        d_rough[s + i] = dr[i];
+      }
+    }
+    if (w.active) {
+      if (p.d_albedo.ptr) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) store_seg<kTexels>(p.d_albedo.ptr + plane_off(p.d_albedo, b, c, w.row, w.col0), w.vec, w.valid, d_albedo[c]);
+      }
+      if (p.normal.ptr && p.d_normal.ptr) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) store_seg<kTexels>(p.d_normal.ptr + plane_off(p.d_normal, b, c, w.row, w.col0), w.vec, w.valid, d_normal[c]);
+      }
+      if (p.d_roughness.ptr) store_seg<kTexels>(p.d_roughness.ptr + plane_off(p.d_roughness, b, 0, w.row, w.col0), w.vec, w.valid, d_rough);
+      if (p.d_metspec.ptr) {
+        constexpr int mc = WF == 0 ? 1 : 3;
+#pragma unroll
+        for (int c = 0; c < mc; ++c) store_seg<kTexels>(p.d_metspec.ptr + plane_off(p.d_metspec, b, c, w.row, w.col0), w.vec, w.valid, d_met[c]);
+      }
+    }
+  }
+
+  if (is_loss) {
+    float sum = warp_sum(loss_local * live);
+    if ((tid & 31) == 0) s_loss[tid >> 5] = sum;
+  }
+  if (is_loss || int_grad) __syncthreads();
+  if (is_loss && tid == 0) {
+    float sum = 0.0f;
+    const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+    for (int i = 0; i < nw; ++i) sum += s_loss[i];
+    atomicAdd(p.loss_sum, sum);
+  }
+  if (int_grad) {
+    for (int i = tid; i < p.flags.L * 3; i += kThreads) atomicAdd(&p.d_intensity[i], s_int[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming kernels: workflow conversions, blend, colour space, normal ingestion
+// ------------------------------------------------------------------------------------------------
+struct ConvKParams {
+  int B, H, W, vec_ok, albedo_is_srgb;
+  PbrPlane albedo, metspec, out0, out1;
+};
+
+template <bool kM2S>
+__global__ void __launch_bounds__(kThreads) convert_kernel(const __grid_constant__ ConvKParams p) {
+  const Where w = locate(p.H, p.W, p.vec_ok != 0);
+  if (!w.active) return;
+  float a[3][kTexels], m[3][kTexels], o0[3][kTexels], o1[3][kTexels];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) load_seg<kTexels>(p.albedo.ptr + plane_off(p.albedo, w.b, c, w.row, w.col0), w.vec, w.valid, a[c]);
+  constexpr int mc = kM2S ? 1 : 3;
+#pragma unroll
+  for (int c = 0; c < mc; ++c) load_seg<kTexels>(p.metspec.ptr + plane_off(p.metspec, w.b, c, w.row, w.col0), w.vec, w.valid, m[c]);
+#pragma unroll
+  for (int i = 0; i < kTexels; ++i) {
+    if (kM2S) {
+      const float a3[3] = {a[0][i], a[1][i], a[2][i]};
+      float d3[3], s3[3];
+      convert_m2s(a3, m[0][i], p.albedo_is_srgb != 0, d3, s3);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { o0[c][i] = d3[c]; o1[c][i] = s3[c]; }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) convert_s2m(a[c][i], m[c][i], p.albedo_is_srgb != 0, &o0[c][i], &o1[c][i]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    store_seg<kTexels>(p.out0.ptr + plane_off(p.out0, w.b, c, w.row, w.col0), w.vec, w.valid, o0[c]);
+    store_seg<kTexels>(p.out1.ptr + plane_off(p.out1, w.b, c, w.row, w.col0), w.vec, w.valid, o1[c]);
+  }
+}
+
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+struct BlendKParams {
+  PbrBlendDesc d;
+  int vec_ok;
+  float width_eps;     // blend_width + 1e-6 (fp32)
+  Linspace grad;       // gradient modes: linspace(0, 1, W or H)
+};
+
+__global__ void __launch_bounds__(kThreads) blend_kernel(const __grid_constant__ BlendKParams p) {
+  const PbrBlendDesc& d = p.d;
+  const Where w = locate(d.H, d.W, p.vec_ok != 0);
+  float mask[kTexels];
+  if (d.mask_mode == PBR_MASK_GIVEN) {
+    load_seg<kTexels>(d.mask.ptr + plane_off(d.mask, w.b, 0, w.row, w.col0), w.vec, w.valid, mask);
+  } else if (d.mask_mode == PBR_MASK_SIGMOID) {
+    float p1[kTexels], p2[kTexels];
+    load_seg<kTexels>(d.prop1.ptr + plane_off(d.prop1, w.b, 0, w.row, w.col0), w.vec, w.valid, p1);
+    load_seg<kTexels>(d.prop2.ptr + plane_off(d.prop2, w.b, 0, w.row, w.col0), w.vec, w.valid, p2);
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i) mask[i] = sigmoid_mask(p1[i], p2[i], d.shift, d.apply_shift != 0, p.width_eps);
+  } else if (d.mask_mode == PBR_MASK_GRADIENT_H) {
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i) {
+      int col = w.col0 + i;
+      mask[i] = linspace_at(p.grad, col < d.W ? col : d.W - 1);
+    }
+  } else {
+    float v = linspace_at(p.grad, w.row);
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i) mask[i] = v;
+  }
+  if (d.mask_mode != PBR_MASK_GIVEN && d.mask_out.ptr && w.active)
+    store_seg<kTexels>(d.mask_out.ptr + plane_off(d.mask_out, w.b, 0, w.row, w.col0), w.vec, w.valid, mask);
+
+  float nmin = INFINITY;
+  for (int m = 0; m < d.n_maps; ++m) {
+    const PbrBlendMap& bm = d.maps[m];
+    if (bm.is_normal) {
+      float a[3][kTexels], b[3][kTexels], o[3][kTexels];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        load_seg<kTexels>(bm.a.ptr + plane_off(bm.a, w.b, c, w.row, w.col0), w.vec, w.valid, a[c]);
+        load_seg<kTexels>(bm.b.ptr + plane_off(bm.b, w.b, c, w.row, w.col0), w.vec, w.valid, b[c]);
+      }
+#pragma unroll
+      for (int i = 0; i < kTexels; ++i) {
+        const float a3[3] = {a[0][i], a[1][i], a[2][i]};
+        const float b3[3] = {b[0][i], b[1][i], b[2][i]};
+        float o3[3];
+        blend_normal(mask[i], a3, b3, o3);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          o[c][i] = o3[c];
+          if (i < w.valid) nmin = fminf(nmin, o3[c]);
+        }
+      }
+      if (w.active) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) store_seg<kTexels>(bm.out.ptr + plane_off(bm.out, w.b, c, w.row, w.col0), w.vec, w.valid, o[c]);
+      }
+    } else {
+      for (int c = 0; c < bm.channels; ++c) {
+        float a[kTexels], b[kTexels], o[kTexels];
+        load_seg<kTexels>(bm.a.ptr + plane_off(bm.a, w.b, c, w.row, w.col0), w.vec, w.valid, a);
+        load_seg<kTexels>(bm.b.ptr + plane_off(bm.b, w.b, c, w.row, w.col0), w.vec, w.valid, b);
+#pragma unroll
+        for (int i = 0; i < kTexels; ++i) o[i] = blend_lerp(mask[i], a[i], b[i]);
+        if (w.active) store_seg<kTexels>(bm.out.ptr + plane_off(bm.out, w.b, c, w.row, w.col0), w.vec, w.valid, o);
+      }
+    }
+  }
+  if (d.normal_min) {
+    if (!w.active) nmin = INFINITY;
+    nmin = warp_min(nmin);
+    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && nmin != INFINITY) atomic_min_float(d.normal_min, nmin);
+  }
+}
+
+struct ColorKParams {
+  int B, C, H, W, vec_ok, to_linear;
+  PbrPlane in, out;
+};
+
+__global__ void __launch_bounds__(kThreads) color_kernel(const __grid_constant__ ColorKParams p) {
+  const Where w = locate(p.H, p.W, p.vec_ok != 0);
+  if (!w.active) return;
+  for (int c = 0; c < p.C; ++c) {
+    float v[kTexels];
+    load_seg<kTexels>(p.in.ptr + plane_off(p.in, w.b, c, w.row, w.col0), w.vec, w.valid, v);
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i) v[i] = p.to_linear ? srgb_decode<false>(v[i], nullptr) : srgb_encode<false>(v[i], nullptr);
+    store_seg<kTexels>(p.out.ptr + plane_off(p.out, w.b, c, w.row, w.col0), w.vec, w.valid, v);
+  }
+}
+
+struct NormalKParams {
+  int B, H, W, vec_ok, channels;
+  PbrPlane in, out;
+  float* result;
+};
+
+__global__ void __launch_bounds__(kThreads) normal_min_kernel(const __grid_constant__ NormalKParams p) {
+  const Where w = locate(p.H, p.W, p.vec_ok != 0);
+  float mn = INFINITY;
+  for (int c = 0; c < p.channels; ++c) {
+    float v[kTexels];
+    load_seg<kTexels>(p.in.ptr + plane_off(p.in, w.b, c, w.row, w.col0), w.vec, w.valid, v);
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i)
+      if (i < w.valid) mn = fminf(mn, v[i]);
+  }
+  if (!w.active) mn = INFINITY;
+  mn = warp_min(mn);
+  if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && mn != INFINITY) atomic_min_float(p.result, mn);
+}
+
+__global__ void __launch_bounds__(kThreads) normal_ingest_kernel(const __grid_constant__ NormalKParams p) {
+  const Where w = locate(p.H, p.W, p.vec_ok != 0);
+  if (!w.active) return;
+  float v[3][kTexels], o[3][kTexels];
+  for (int c = 0; c < p.channels; ++c) load_seg<kTexels>(p.in.ptr + plane_off(p.in, w.b, c, w.row, w.col0), w.vec, w.valid, v[c]);
+#pragma unroll
+  for (int i = 0; i < kTexels; ++i) {
+    float o3[3];
+    if (p.channels == 3) {
+      const float v3[3] = {v[0][i], v[1][i], v[2][i]};
+      ingest_normal3(v3, o3);
+    } else {
+      const float v2[2] = {v[0][i], v[1][i]};
+      ingest_normal2(v2, o3);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c][i] = o3[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) store_seg<kTexels>(p.out.ptr + plane_off(p.out, w.b, c, w.row, w.col0), w.vec, w.valid, o[c]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side of the C ABI
+// ------------------------------------------------------------------------------------------------
+static bool plane_vec_ok(const PbrPlane& pl) {
+  if (!pl.ptr) return true;
+  return (reinterpret_cast<uintptr_t>(pl.ptr) % 16 == 0) && (pl.sb % 4 == 0) && (pl.sc % 4 == 0) && (pl.sh % 4 == 0);
+}
+
+static void launch_shape(int B, int H, int W, dim3& grid, dim3& block) {
+  int groups = (W + kTexels - 1) / kTexels;
+  int bx = 1;
+  while (bx < groups && bx < 64) bx <<= 1;  // 1..64 thread columns
+  int by = kThreads / bx;
+  block = dim3(bx, by, 1);
+  grid = dim3((groups + bx - 1) / bx, (H + by - 1) / by, B);
+}
+
+static int check_dims(int B, int H, int W) {
+  if (B < 1 || H < 1 || W < 1 || B > 65535 || H > 65535 * 4) return PBR_E_SHAPE;  // grid.z = B, grid.y = ceil(H / blockDim.y), blockDim.y >= 4
+  return PBR_OK;
+}
+
+static int fill_ct_params(const PbrCtDesc* d, CtKParams& k) {
+  if (!d) return PBR_E_NULL;
+  if (int rc = check_dims(d->B, d->H, d->W)) return rc;
+  if (d->L < 1) return PBR_E_SHAPE;
+  if (d->L > PBR_MAX_LIGHTS) return PBR_E_TOO_MANY;
+  if (d->workflow != PBR_WORKFLOW_METALLIC && d->workflow != PBR_WORKFLOW_SPECULAR) return PBR_E_ENUM;
+  if (d->metallic_channels != 0 && d->metallic_channels != 1 && d->metallic_channels != 3) return PBR_E_CHANNELS;
+  if (d->light_type != PBR_LIGHT_DIRECTIONAL && d->light_type != PBR_LIGHT_POINT) return PBR_E_ENUM;
+  if (!d->albedo.ptr || !d->roughness.ptr || !d->metspec.ptr || !d->view || !d->lights || !d->intensity) return PBR_E_NULL;
+  k.B = d->B; k.H = d->H; k.W = d->W;
+  k.flags.L = d->L;
+  k.flags.point = d->light_type == PBR_LIGHT_POINT;
+  k.flags.albedo_is_srgb = d->albedo_is_srgb != 0;
+  k.flags.specular_is_srgb = d->specular_is_srgb != 0;
+  k.flags.return_srgb = d->return_srgb != 0;
+  k.flags.per_light = d->per_light != 0;
+  k.albedo = d->albedo; k.normal = d->normal; k.roughness = d->roughness; k.metspec = d->metspec;
+  k.out = d->out; k.out_sl = d->out_sl;
+  k.vec_ok = plane_vec_ok(d->albedo) && plane_vec_ok(d->normal) && plane_vec_ok(d->roughness) && plane_vec_ok(d->metspec);
+  const float s = d->light_size > 0.0f ? d->light_size : 1.0f;  // `light_size or 1.0`, cooktorrance.py:130
+  k.lsx = make_linspace(-s / 2, s / 2, d->W);
+  k.lsy = make_linspace(-s / 2, s / 2, d->H);
+  if (d->params_on_device) {
+    k.view_dev = d->view; k.lights_dev = d->lights; k.inten_dev = d->intensity;
+  } else {
+    k.view_dev = nullptr; k.lights_dev = nullptr; k.inten_dev = nullptr;
+    for (int i = 0; i < 3; ++i) k.view[i] = d->view[i];
+    for (int i = 0; i < 3 * d->L; ++i) { k.lights[i] = d->lights[i]; k.inten[i] = d->intensity[i]; }
+  }
+  return PBR_OK;
+}
+
+static int launch_result() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  return e == cudaSuccess ? PBR_OK : (int)e;
+}
+
+// Point light with L == 1: the light geometry of a texel is shared by every material of the batch,
+// so a thread walks over up to kHoistMats materials and computes it once.
+constexpr int kHoistMats = 4;
+
+static int light_mode(const CtKParams& k) {
+  if (!k.flags.point) return kLightDirectional;
+  return k.flags.L == 1 ? kLightPointHoisted : kLightPoint;
+}
+
+static void ct_launch_shape(CtKParams& k, dim3& grid, dim3& block) {
+  launch_shape(k.B, k.H, k.W, grid, block);
+  k.mats_per_cta = (light_mode(k) == kLightPointHoisted) ? (k.B < kHoistMats ? k.B : kHoistMats) : 1;
+  grid.z = (k.B + k.mats_per_cta - 1) / k.mats_per_cta;
+}
+
+// kernel workflow index: 0 metallic (1-channel map), 1 specular, 2 metallic with a 3-channel map
+static int kernel_workflow(const PbrCtDesc* d) {
+  if (d->workflow == PBR_WORKFLOW_SPECULAR) return 1;
+  return d->metallic_channels == 3 ? 2 : 0;
+}
+
+template <int WF>
+static void launch_fwd(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t st) {
+  switch (light_mode(k)) {
+    case kLightDirectional: ct_forward_kernel<WF, kLightDirectional><<<grid, block, 0, st>>>(k); break;
+    case kLightPoint: ct_forward_kernel<WF, kLightPoint><<<grid, block, 0, st>>>(k); break;
+    default: ct_forward_kernel<WF, kLightPointHoisted><<<grid, block, 0, st>>>(k); break;
+  }
+}
+
+template <int WF>
+static void launch_bwd(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t st) {
+  switch (light_mode(k)) {
+    case kLightDirectional: ct_backward_kernel<WF, kLightDirectional><<<grid, block, 0, st>>>(k); break;
+    case kLightPoint: ct_backward_kernel<WF, kLightPoint><<<grid, block, 0, st>>>(k); break;
+    default: ct_backward_kernel<WF, kLightPointHoisted><<<grid, block, 0, st>>>(k); break;
+  }
+}
+
+static int fill_grads(const PbrCtGrads* g, CtKParams& k) {
+  if (!g) return PBR_E_NULL;
+  k.d_albedo = g->d_albedo; k.d_normal = g->d_normal; k.d_roughness = g->d_roughness; k.d_metspec = g->d_metspec;
+  k.d_intensity = g->d_intensity;
+  k.vec_ok = k.vec_ok && plane_vec_ok(g->d_albedo) && plane_vec_ok(g->d_normal) && plane_vec_ok(g->d_roughness) &&
+             plane_vec_ok(g->d_metspec);
+  return PBR_OK;
+}
+
+}  // namespace pbr
+
+using namespace pbr;
+
+extern "C" {
+
+int pbr_abi_version(void) { return PBR_ABI_VERSION; }
+
+const char* pbr_strerror(int code) {
+  switch (code) {
+    case PBR_OK: return "ok";
+    case PBR_E_NULL: return "required pointer is NULL";
+    case PBR_E_SHAPE: return "B/H/W/L out of range";
+    case PBR_E_ENUM: return "workflow / light_type / mode out of range";
+    case PBR_E_TOO_MANY: return "too many lights or maps for one launch";
+    case PBR_E_CHANNELS: return "unsupported channel count";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown pbr error";
+  }
+}
+
+uint64_t pbr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int pbr_ct_forward(const PbrCtDesc* desc, pbr_stream_t stream) {
+  CtKParams k{};
+  if (int rc = fill_ct_params(desc, k)) return rc;
+  if (!desc->out.ptr) return PBR_E_NULL;
+  k.vec_ok = k.vec_ok && plane_vec_ok(desc->out) && (desc->out_sl % 4 == 0);
+  dim3 grid, block;
+  ct_launch_shape(k, grid, block);
+  switch (kernel_workflow(desc)) {
+    case 0: launch_fwd<0>(k, grid, block, (cudaStream_t)stream); break;
+    case 1: launch_fwd<1>(k, grid, block, (cudaStream_t)stream); break;
+    default: launch_fwd<2>(k, grid, block, (cudaStream_t)stream); break;
+  }
+  return launch_result();
+}
+
+int pbr_ct_backward(const PbrCtDesc* desc, const PbrCtGrads* grads, pbr_stream_t stream) {
+  CtKParams k{};
+  if (int rc = fill_ct_params(desc, k)) return rc;
+  if (int rc = fill_grads(grads, k)) return rc;
+  if (!grads->grad_out.ptr) return PBR_E_NULL;
+  k.gsrc = grads->grad_out; k.gsrc_sl = grads->grad_out_sl;
+  k.is_loss = 0;
+  k.vec_ok = k.vec_ok && plane_vec_ok(grads->grad_out) && (grads->grad_out_sl % 4 == 0);
+  dim3 grid, block;
+  ct_launch_shape(k, grid, block);
+  switch (kernel_workflow(desc)) {
+    case 0: launch_bwd<0>(k, grid, block, (cudaStream_t)stream); break;
+    case 1: launch_bwd<1>(k, grid, block, (cudaStream_t)stream); break;
+    default: launch_bwd<2>(k, grid, block, (cudaStream_t)stream); break;
+  }
+  return launch_result();
+}
+
+int pbr_ct_loss_fwd_bwd(const PbrCtDesc* desc, const PbrCtLoss* loss, const PbrCtGrads* grads, pbr_stream_t stream) {
+  CtKParams k{};
+  if (int rc = fill_ct_params(desc, k)) return rc;
+  if (int rc = fill_grads(grads, k)) return rc;
+  if (!loss || !loss->target.ptr || !loss->loss_sum) return PBR_E_NULL;
+  k.gsrc = loss->target; k.gsrc_sl = loss->target_sl;
+  k.is_loss = 1;
+  k.loss_scale = loss->loss_scale; k.loss_sum = loss->loss_sum;
+  k.vec_ok = k.vec_ok && plane_vec_ok(loss->target) && (loss->target_sl % 4 == 0);
+  dim3 grid, block;
+  ct_launch_shape(k, grid, block);
+  switch (kernel_workflow(desc)) {
+    case 0: launch_bwd<0>(k, grid, block, (cudaStream_t)stream); break;
+    case 1: launch_bwd<1>(k, grid, block, (cudaStream_t)stream); break;
+    default: launch_bwd<2>(k, grid, block, (cudaStream_t)stream); break;
+  }
+  return launch_result();
+}
+
+static int run_convert(const PbrConvDesc* d, bool m2s, pbr_stream_t stream) {
+  if (!d) return PBR_E_NULL;
+  if (int rc = check_dims(d->B, d->H, d->W)) return rc;
+  if (!d->albedo.ptr || !d->metspec.ptr || !d->out0.ptr || !d->out1.ptr) return PBR_E_NULL;
+  ConvKParams k{};
+  k.B = d->B; k.H = d->H; k.W = d->W; k.albedo_is_srgb = d->albedo_is_srgb;
+  k.albedo = d->albedo; k.metspec = d->metspec; k.out0 = d->out0; k.out1 = d->out1;
+  k.vec_ok = plane_vec_ok(d->albedo) && plane_vec_ok(d->metspec) && plane_vec_ok(d->out0) && plane_vec_ok(d->out1);
+  dim3 grid, block;
+  launch_shape(k.B, k.H, k.W, grid, block);
+  if (m2s) convert_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(k);
+  else convert_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(k);
+  return launch_result();
+}
+
+int pbr_convert_m2s(const PbrConvDesc* desc, pbr_stream_t stream) { return run_convert(desc, true, stream); }
+int pbr_convert_s2m(const PbrConvDesc* desc, pbr_stream_t stream) { return run_convert(desc, false, stream); }
+
+int pbr_blend(const PbrBlendDesc* d, pbr_stream_t stream) {
+  if (!d) return PBR_E_NULL;
+  if (int rc = check_dims(d->B, d->H, d->W)) return rc;
+  if (d->n_maps < 0) return PBR_E_SHAPE;
+  if (d->n_maps > PBR_MAX_BLEND_MAPS) return PBR_E_TOO_MANY;
+  if (d->mask_mode < PBR_MASK_GIVEN || d->mask_mode > PBR_MASK_GRADIENT_V) return PBR_E_ENUM;
+  if (d->mask_mode == PBR_MASK_GIVEN && !d->mask.ptr) return PBR_E_NULL;
+  if (d->mask_mode == PBR_MASK_SIGMOID && (!d->prop1.ptr || !d->prop2.ptr)) return PBR_E_NULL;
+  BlendKParams k{};
+  k.d = *d;
+  bool vec = plane_vec_ok(d->mask) && plane_vec_ok(d->prop1) && plane_vec_ok(d->prop2) && plane_vec_ok(d->mask_out);
+  if (d->mask_mode != PBR_MASK_GIVEN) k.d.mask.ptr = nullptr;
+  for (int m = 0; m < d->n_maps; ++m) {
+    const PbrBlendMap& bm = d->maps[m];
+    if (!bm.a.ptr || !bm.b.ptr || !bm.out.ptr) return PBR_E_NULL;
+    if (bm.channels < 1 || bm.channels > 4 || (bm.is_normal && bm.channels != 3)) return PBR_E_CHANNELS;
+    vec = vec && plane_vec_ok(bm.a) && plane_vec_ok(bm.b) && plane_vec_ok(bm.out);
+  }
+  k.vec_ok = vec;
+  k.width_eps = d->blend_width + 1e-6f;
+  if (d->mask_mode == PBR_MASK_GRADIENT_H) k.grad = make_linspace(0.0f, 1.0f, d->W);
+  if (d->mask_mode == PBR_MASK_GRADIENT_V) k.grad = make_linspace(0.0f, 1.0f, d->H);
+  dim3 grid, block;
+  launch_shape(d->B, d->H, d->W, grid, block);
+  blend_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);
+  return launch_result();
+}
+
+int pbr_color_convert(const PbrColorDesc* d, pbr_stream_t stream) {
+  if (!d) return PBR_E_NULL;
+  if (int rc = check_dims(d->B, d->H, d->W)) return rc;
+  if (d->C < 1) return PBR_E_CHANNELS;
+  if (!d->in.ptr || !d->out.ptr) return PBR_E_NULL;
+  ColorKParams k{};
+  k.B = d->B; k.C = d->C; k.H = d->H; k.W = d->W; k.to_linear = d->to_linear;
+  k.in = d->in; k.out = d->out;
+  k.vec_ok = plane_vec_ok(d->in) && plane_vec_ok(d->out);
+  dim3 grid, block;
+  launch_shape(k.B, k.H, k.W, grid, block);
+  color_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);
+  return launch_result();
+}
+
+static int fill_normal(const PbrNormalDesc* d, NormalKParams& k, bool need_out) {
+  if (!d) return PBR_E_NULL;
+  if (int rc = check_dims(d->B, d->H, d->W)) return rc;
+  if (d->channels != 2 && d->channels != 3) return PBR_E_CHANNELS;
+  if (!d->in.ptr || (need_out && !d->out.ptr)) return PBR_E_NULL;
+  k.B = d->B; k.H = d->H; k.W = d->W; k.channels = d->channels;
+  k.in = d->in; k.out = d->out;
+  k.vec_ok = plane_vec_ok(d->in) && (!need_out || plane_vec_ok(d->out));
+  return PBR_OK;
+}
+
+int pbr_normal_min(const PbrNormalDesc* d, float* result, pbr_stream_t stream) {
+  NormalKParams k{};
+  if (int rc = fill_normal(d, k, false)) return rc;
+  if (!result) return PBR_E_NULL;
+  k.result = result;
+  dim3 grid, block;
+  launch_shape(k.B, k.H, k.W, grid, block);
+  normal_min_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);
+  return launch_result();
+}
+
+int pbr_normal_ingest(const PbrNormalDesc* d, pbr_stream_t stream) {
+  NormalKParams k{};
+  if (int rc = fill_normal(d, k, true)) return rc;
+  dim3 grid, block;
+  launch_shape(k.B, k.H, k.W, grid, block);
+  normal_ingest_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);
+  return launch_result();
+}
+
+}  // extern "C"

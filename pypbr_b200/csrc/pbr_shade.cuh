@@ -1,0 +1,254 @@
+// pbr_shade.cuh — staging of the view / light parameters and the per-thread drivers that shade a
+// group of N texels (N consecutive columns of one row) over L lights, forward and backward.
+// Used by the CUDA kernels (N = texels per thread, CtStage in shared memory) and by the host
+// build of the CPU test-suite (N = 1).
+#pragma once
+
+#include "pbr_math.cuh"
+
+#ifndef PBR_MAX_LIGHTS
+#define PBR_MAX_LIGHTS 64
+#endif
+
+namespace pbr {
+
+struct CtLight {
+  float p[3];      // point: position; directional: raw direction
+  float inten[3];
+  LightGeom geom;  // directional lights: complete geometry (constant over the image)
+};
+
+// What the kernel prologue stages in shared memory.
+struct CtStage {
+  float vx, vy, vz;  // F.normalize(view_dir), cooktorrance.py:95
+  Linspace lsx, lsy; // the plane grid of cooktorrance.py:132-133
+  CtLight light[PBR_MAX_LIGHTS];
+};
+
+struct CtFlags {
+  int L;
+  bool point;             // light_type == point
+  bool albedo_is_srgb, specular_is_srgb, return_srgb, per_light;
+};
+
+PBR_HD void stage_view(const float* view, float& vx, float& vy, float& vz) {
+  float dn = fmaxf(xnorm3(view[0], view[1], view[2]), kNormEps);
+  vx = xdiv(view[0], dn);
+  vy = xdiv(view[1], dn);
+  vz = xdiv(view[2], dn);
+}
+
+PBR_HD void stage_light(int l, const float* lights, const float* inten, bool point, float vx, float vy, float vz,
+                        CtLight& out) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    out.p[c] = lights[3 * l + c];
+    out.inten[c] = inten[3 * l + c];
+  }
+  if (!point) dir_light_geom(out.p[0], out.p[1], out.p[2], vx, vy, vz, out.geom);
+}
+
+// torch.linspace(-s/2, s/2, n) parameters, computed once on the host.
+inline Linspace make_linspace(float start, float end, int n) {
+  Linspace ls;
+  ls.start = start;
+  ls.end = end;
+  ls.n = n;
+  if (n <= 1) {  // aten fills [start]
+    ls.step = 0.0f;
+    ls.half = 1;
+  } else {
+    ls.step = (end - start) / (float)(n - 1);
+    ls.half = n / 2;
+  }
+  return ls;
+}
+
+// How the per-texel light geometry is obtained.
+enum LightMode {
+  kLightDirectional = 0,  // constant over the image: read from the stage
+  kLightPoint = 1,        // computed per texel and per light
+  kLightPointHoisted = 2  // point light, L == 1: computed once per texel by the caller and reused for
+                          // every material of the batch the thread walks over (geometry does not
+                          // depend on the material)
+};
+
+template <int kLight, int N>
+PBR_HD void light_geom(const CtStage& S, int l, const float (&x)[N], float y, const LightGeom (&hoisted)[N], int i,
+                       LightGeom& g) {
+  if (kLight == kLightPoint) {
+    point_light_geom(S.light[l].p[0], S.light[l].p[1], S.light[l].p[2], x[i], y, S.vx, S.vy, S.vz, g);
+  } else if (kLight == kLightPointHoisted) {
+    g = hoisted[i];
+  } else {
+    g = S.light[l].geom;
+  }
+}
+
+PBR_HD float encode_out(float c, bool return_srgb) { return return_srgb ? srgb_encode<false>(c, nullptr) : c; }
+PBR_HD float encode_out_d(float c, bool return_srgb, float* d) {
+  if (return_srgb) return srgb_encode<true>(c, d);
+  *d = 1.0f;
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: N texels of one row.  emit(l, out[3][N]) receives the encoded colour of light l
+// (per-light mode) or, once, of the accumulated image (l = 0).
+// ------------------------------------------------------------------------------------------------
+template <int kWorkflow, int kLight, int N, class Emit>
+PBR_HD void ct_forward_group(const CtStage& S, const CtFlags& F, const float (&araw)[3][N], const float (&nraw)[3][N],
+                             const float (&rough)[N], const float (&mraw)[3][N], const float (&x)[N], float y,
+                             const LightGeom (&hoisted)[N], Emit emit) {
+  Texel<kWorkflow> t[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float a3[3] = {araw[0][i], araw[1][i], araw[2][i]};
+    const float n3[3] = {nraw[0][i], nraw[1][i], nraw[2][i]};
+    const float m3[3] = {mraw[0][i], mraw[1][i], mraw[2][i]};
+    texel_setup<kWorkflow, false>(a3, n3, rough[i], m3, F.albedo_is_srgb, F.specular_is_srgb, S.vx, S.vy, S.vz, t[i]);
+  }
+  float acc[3][N];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc[c][i] = 0.0f;
+
+  const int L = (kLight == kLightPointHoisted) ? 1 : F.L;
+  for (int l = 0; l < L; ++l) {
+    float outv[3][N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      LightGeom g;
+      light_geom<kLight, N>(S, l, x, y, hoisted, i, g);
+      LightFwd f;
+      float col[3];
+      shade_light_fwd<kWorkflow>(t[i], g, S.light[l].inten, f, col);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (F.per_light) outv[c][i] = encode_out(col[c], F.return_srgb);
+        else acc[c][i] = xadd(acc[c][i], col[c]);
+      }
+    }
+    if (F.per_light) emit(l, outv);
+  }
+  if (!F.per_light) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < N; ++i) acc[c][i] = encode_out(clamp01(acc[c][i]), F.return_srgb);
+    emit(0, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: N texels of one row.
+//   gout(l, out[3][N], g[3][N]) : given the encoded output of light l (or of the accumulated image,
+//        l = 0) fills g = dLoss/d out.  The plain backward ignores `out` and loads grad_out; the fused
+//        loss kernel computes 2*scale*(out - target) and accumulates the loss.
+//   int_sink(l, g_int[3])       : per-light intensity gradient summed over the N texels.
+// Results: d_albedo/d_normal/d_met [3][N], d_rough[N].
+// ------------------------------------------------------------------------------------------------
+template <int kWorkflow, int kLight, int N, class Gout, class IntSink>
+PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const float (&araw)[3][N],
+                              const float (&nraw)[3][N], const float (&rough)[N], const float (&mraw)[3][N],
+                              const float (&x)[N], float y, const LightGeom (&hoisted)[N], Gout gout,
+                              IntSink int_sink, float (&d_albedo)[3][N], float (&d_normal)[3][N],
+                              float (&d_rough)[N], float (&d_met)[3][N]) {
+  Texel<kWorkflow> t[N];
+  TexelGrad tg[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float a3[3] = {araw[0][i], araw[1][i], araw[2][i]};
+    const float n3[3] = {nraw[0][i], nraw[1][i], nraw[2][i]};
+    const float m3[3] = {mraw[0][i], mraw[1][i], mraw[2][i]};
+    texel_setup<kWorkflow, true>(a3, n3, rough[i], m3, F.albedo_is_srgb, F.specular_is_srgb, S.vx, S.vy, S.vz, t[i]);
+    texel_grad_zero(tg[i]);
+  }
+
+  const int L = (kLight == kLightPointHoisted) ? 1 : F.L;
+  const bool two_pass = (!F.per_light) && L > 1;
+  float g_tot[3][N];  // two-pass only: gradient w.r.t. every per-light colour
+  if (two_pass) {
+    // pass 1: the accumulated image, to know where clamp(sum) gates and the slope of the encode
+    float acc[3][N];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < N; ++i) acc[c][i] = 0.0f;
+    for (int l = 0; l < L; ++l) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        LightGeom g;
+        light_geom<kLight, N>(S, l, x, y, hoisted, i, g);
+        LightFwd f;
+        float col[3];
+        shade_light_fwd<kWorkflow>(t[i], g, S.light[l].inten, f, col);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c][i] = xadd(acc[c][i], col[c]);
+      }
+    }
+    float outv[3][N], slope[3][N];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        outv[c][i] = encode_out_d(clamp01(acc[c][i]), F.return_srgb, &slope[c][i]);
+        slope[c][i] *= gate01(acc[c][i]);
+      }
+    gout(0, outv, g_tot);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < N; ++i) g_tot[c][i] *= slope[c][i];
+  }
+
+  for (int l = 0; l < L; ++l) {
+    LightGeom g[N];
+    LightFwd f[N];
+    float outv[3][N], slope[3][N], gl[3][N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      light_geom<kLight, N>(S, l, x, y, hoisted, i, g[i]);
+      float col[3];
+      shade_light_fwd<kWorkflow>(t[i], g[i], S.light[l].inten, f[i], col);
+      if (!two_pass) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) outv[c][i] = encode_out_d(col[c], F.return_srgb, &slope[c][i]);
+      }
+    }
+    if (!two_pass) {
+      gout(l, outv, gl);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int i = 0; i < N; ++i) gl[c][i] *= slope[c][i];
+    }
+    float gi_sum[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float gc[3] = {two_pass ? g_tot[0][i] : gl[0][i], two_pass ? g_tot[1][i] : gl[1][i],
+                           two_pass ? g_tot[2][i] : gl[2][i]};
+      float gi[3];
+      shade_light_bwd<kWorkflow>(t[i], g[i], S.light[l].inten, f[i], gc, tg[i], gi);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gi_sum[c] += gi[c];
+    }
+    int_sink(l, gi_sum);
+  }
+
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float da[3], dn[3], dm[3], dr;
+    texel_finish_grad<kWorkflow>(t[i], tg[i], rough[i], S.vx, S.vy, S.vz, da, dn, &dr, dm);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      d_albedo[c][i] = da[c];
+      d_normal[c][i] = dn[c];
+      d_met[c][i] = dm[c];
+    }
+    d_rough[i] = dr;
+  }
+}
+
+}  // namespace pbr
