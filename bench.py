@@ -88,7 +88,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def __enter__(self):
         self.t.start()

@@ -17,8 +17,23 @@
 
 namespace pbr {
 
-constexpr int kTexels = 4;      // texels per thread (one float4 per plane)
-constexpr int kThreads = 256;   // threads per CTA
+#ifndef PBR_THREADS
+#define PBR_THREADS 256
+#endif
+#ifndef PBR_FWD_MIN_CTAS
+#define PBR_FWD_MIN_CTAS 3   // __launch_bounds__ minBlocksPerSM hints (register caps), tuned on the GPU (profiles/)
+#endif
+#ifndef PBR_BWD_MIN_CTAS
+#define PBR_BWD_MIN_CTAS 2
+#endif
+#ifndef PBR_HOIST_MATS
+#define PBR_HOIST_MATS 16    // materials a thread walks over when the light geometry is hoisted
+#endif
+#ifndef PBR_TEXELS
+#define PBR_TEXELS 4         // texels per thread: 4 (float4 per plane), 2 (float2) or 1 (scalar, coalesced per warp)
+#endif
+constexpr int kTexels = PBR_TEXELS;     // texels per thread
+constexpr int kThreads = PBR_THREADS;   // threads per CTA
 
 static std::atomic<uint64_t> g_launches{0};
 
@@ -35,7 +50,7 @@ __device__ __forceinline__ void load_seg(const float* __restrict__ p, bool vec, 
     dst[0] = v.x; dst[1] = v.y;
   } else {
 #pragma unroll
-    for (int i = 0; i < N; ++i) dst[i] = __ldcs(p + (i < valid ? i : (valid > 0 ? valid - 1 : 0)));
+    for (int i = 0; i < N; ++i) dst[i] = __ldcs(p + (i < valid ? i : (valid > 0 ? valid - 1 : 0)));  // N == 1 lands here
   }
 }
 
@@ -80,10 +95,10 @@ __device__ __forceinline__ Where locate(int H, int W, bool vec_ok) {
 // Cook-Torrance kernels
 // ------------------------------------------------------------------------------------------------
 #ifndef PBR_FWD_GROUP
-#define PBR_FWD_GROUP 4   // texels shaded together (ILP) by the forward kernel: 1, 2 or 4
+#define PBR_FWD_GROUP (PBR_TEXELS > 2 ? 2 : PBR_TEXELS)   // texels shaded together (ILP) by the forward kernel
 #endif
 #ifndef PBR_BWD_GROUP
-#define PBR_BWD_GROUP 2   // ... by the backward kernel (register pressure: 2)
+#define PBR_BWD_GROUP 1   // ... by the backward kernel (register pressure)
 #endif
 
 struct CtKParams {
@@ -180,7 +195,7 @@ __device__ __forceinline__ void slice3(const float (&src)[3][N], int s, float (&
 }
 
 template <int WF, int kLight>
-__global__ void __launch_bounds__(kThreads) ct_forward_kernel(const __grid_constant__ CtKParams p) {
+__global__ void __launch_bounds__(kThreads, PBR_FWD_MIN_CTAS) ct_forward_kernel(const __grid_constant__ CtKParams p) {
   constexpr int G = PBR_FWD_GROUP;
   __shared__ CtStage S;
   stage_params(p, S);
@@ -241,7 +256,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 //                   error is reduced warp-shuffle -> shared -> ONE atomic per CTA.
 //   p.d_intensity : per-light intensity gradients, reduced the same way.
 template <int WF, int kLight>
-__global__ void __launch_bounds__(kThreads) ct_backward_kernel(const __grid_constant__ CtKParams p) {
+__global__ void __launch_bounds__(kThreads, PBR_BWD_MIN_CTAS) ct_backward_kernel(const __grid_constant__ CtKParams p) {
   constexpr int G = PBR_BWD_GROUP;
   __shared__ CtStage S;
   __shared__ float s_int[PBR_MAX_LIGHTS * 3];
@@ -533,22 +548,28 @@ __global__ void __launch_bounds__(kThreads) normal_ingest_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------------
 // host side of the C ABI
 // ------------------------------------------------------------------------------------------------
+// vector access of kTexels floats is legal when the base pointer and every stride keep that alignment
 static bool plane_vec_ok(const PbrPlane& pl) {
-  if (!pl.ptr) return true;
-  return (reinterpret_cast<uintptr_t>(pl.ptr) % 16 == 0) && (pl.sb % 4 == 0) && (pl.sc % 4 == 0) && (pl.sh % 4 == 0);
+  if (!pl.ptr || kTexels == 1) return true;
+  return (reinterpret_cast<uintptr_t>(pl.ptr) % (4 * kTexels) == 0) && (pl.sb % kTexels == 0) && (pl.sc % kTexels == 0) &&
+         (pl.sh % kTexels == 0);
 }
+
+// A CTA covers a strip of up to 256 texels of blockDim.y consecutive rows.
+constexpr int kMaxBx = 256 / kTexels < kThreads ? 256 / kTexels : kThreads;
+constexpr int kMinBy = kThreads / kMaxBx;
 
 static void launch_shape(int B, int H, int W, dim3& grid, dim3& block) {
   int groups = (W + kTexels - 1) / kTexels;
   int bx = 1;
-  while (bx < groups && bx < 64) bx <<= 1;  // 1..64 thread columns
+  while (bx < groups && bx < kMaxBx) bx <<= 1;
   int by = kThreads / bx;
   block = dim3(bx, by, 1);
   grid = dim3((groups + bx - 1) / bx, (H + by - 1) / by, B);
 }
 
 static int check_dims(int B, int H, int W) {
-  if (B < 1 || H < 1 || W < 1 || B > 65535 || H > 65535 * 4) return PBR_E_SHAPE;  // grid.z = B, grid.y = ceil(H / blockDim.y), blockDim.y >= 4
+  if (B < 1 || H < 1 || W < 1 || B > 65535 || H > 65535 * kMinBy) return PBR_E_SHAPE;  // grid.z = ceil(B / mats), grid.y = ceil(H / blockDim.y), blockDim.y >= kMinBy
   return PBR_OK;
 }
 
@@ -592,7 +613,7 @@ static int launch_result() {
 
 // Point light with L == 1: the light geometry of a texel is shared by every material of the batch,
 // so a thread walks over up to kHoistMats materials and computes it once.
-constexpr int kHoistMats = 4;
+constexpr int kHoistMats = PBR_HOIST_MATS;
 
 static int light_mode(const CtKParams& k) {
   if (!k.flags.point) return kLightDirectional;
@@ -664,7 +685,7 @@ int pbr_ct_forward(const PbrCtDesc* desc, pbr_stream_t stream) {
   CtKParams k{};
   if (int rc = fill_ct_params(desc, k)) return rc;
   if (!desc->out.ptr) return PBR_E_NULL;
-  k.vec_ok = k.vec_ok && plane_vec_ok(desc->out) && (desc->out_sl % 4 == 0);
+  k.vec_ok = k.vec_ok && plane_vec_ok(desc->out) && (desc->out_sl % kTexels == 0);
   dim3 grid, block;
   ct_launch_shape(k, grid, block);
   switch (kernel_workflow(desc)) {
@@ -682,7 +703,7 @@ int pbr_ct_backward(const PbrCtDesc* desc, const PbrCtGrads* grads, pbr_stream_t
   if (!grads->grad_out.ptr) return PBR_E_NULL;
   k.gsrc = grads->grad_out; k.gsrc_sl = grads->grad_out_sl;
   k.is_loss = 0;
-  k.vec_ok = k.vec_ok && plane_vec_ok(grads->grad_out) && (grads->grad_out_sl % 4 == 0);
+  k.vec_ok = k.vec_ok && plane_vec_ok(grads->grad_out) && (grads->grad_out_sl % kTexels == 0);
   dim3 grid, block;
   ct_launch_shape(k, grid, block);
   switch (kernel_workflow(desc)) {
@@ -701,7 +722,7 @@ int pbr_ct_loss_fwd_bwd(const PbrCtDesc* desc, const PbrCtLoss* loss, const PbrC
   k.gsrc = loss->target; k.gsrc_sl = loss->target_sl;
   k.is_loss = 1;
   k.loss_scale = loss->loss_scale; k.loss_sum = loss->loss_sum;
-  k.vec_ok = k.vec_ok && plane_vec_ok(loss->target) && (loss->target_sl % 4 == 0);
+  k.vec_ok = k.vec_ok && plane_vec_ok(loss->target) && (loss->target_sl % kTexels == 0);
   dim3 grid, block;
   ct_launch_shape(k, grid, block);
   switch (kernel_workflow(desc)) {

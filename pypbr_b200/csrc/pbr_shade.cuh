@@ -194,7 +194,7 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const float (&
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         outv[c][i] = encode_out_d(clamp01(acc[c][i]), F.return_srgb, &slope[c][i]);
-        slope[c][i] *= gate01(acc[c][i]);
+        slope[c][i] = gated(slope[c][i], acc[c][i], clamp01(acc[c][i]));
       }
     gout(0, outv, g_tot);
 #pragma unroll
