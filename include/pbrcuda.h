@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PBR_ABI_VERSION 1
+#define PBR_ABI_VERSION 2
 #define PBR_MAX_LIGHTS 64      /* lights per launch (parameters are staged in shared memory) */
 #define PBR_MAX_BLEND_MAPS 12  /* maps blended by one pbr_blend launch */
 
@@ -78,6 +78,8 @@ typedef struct PbrCtDesc {
   const float* intensity;   /* L*3 */
   PbrPlane out;             /* 3 ch; per_light: sb is the stride of b, `out_sl` the stride of l */
   int64_t out_sl;
+  int32_t force_generic;    /* 0: pick the kernel automatically (streamed TMA-fed kernels for L == 1 on 16-byte aligned,
+                               W % 4 == 0 maps; generic kernels otherwise); 1: always the generic kernels (A/B tests) */
 } PbrCtDesc;
 
 /* Gradient buffers for pbr_ct_backward.  Any d_* with ptr == NULL is not computed. */
@@ -178,6 +180,11 @@ int pbr_blend(const PbrBlendDesc* desc, pbr_stream_t stream);
 int pbr_color_convert(const PbrColorDesc* desc, pbr_stream_t stream);
 int pbr_normal_min(const PbrNormalDesc* desc, float* result, pbr_stream_t stream);
 int pbr_normal_ingest(const PbrNormalDesc* desc, pbr_stream_t stream);
+
+/* sizeof() of the descriptor structs as THIS library was compiled (binding self-check):
+   which = 0 PbrPlane, 1 PbrCtDesc, 2 PbrCtGrads, 3 PbrCtLoss, 4 PbrConvDesc, 5 PbrBlendMap, 6 PbrBlendDesc,
+   7 PbrColorDesc, 8 PbrNormalDesc; anything else returns 0. */
+uint64_t pbr_sizeof(int which);
 
 /* Number of kernel launches this process has enqueued through the library (for bench accounting). */
 uint64_t pbr_launch_count(void);

@@ -16,6 +16,7 @@ from typing import Optional, Sequence
 
 import torch
 
+ABI_VERSION = 2
 PBR_MAX_LIGHTS = 64
 PBR_MAX_BLEND_MAPS = 12
 
@@ -41,6 +42,7 @@ class PbrCtDesc(Structure):
         ("metallic_channels", c_int32),
         ("view", c_void_p), ("lights", c_void_p), ("intensity", c_void_p),
         ("out", PbrPlane), ("out_sl", c_int64),
+        ("force_generic", c_int32),
     ]
 
 
@@ -88,13 +90,16 @@ class PbrNormalDesc(Structure):
     _fields_ = [("B", c_int32), ("H", c_int32), ("W", c_int32), ("channels", c_int32), ("in_", PbrPlane), ("out", PbrPlane)]
 
 
+# order = the `which` argument of pbr_sizeof()
+STRUCTS = (PbrPlane, PbrCtDesc, PbrCtGrads, PbrCtLoss, PbrConvDesc, PbrBlendMap, PbrBlendDesc, PbrColorDesc, PbrNormalDesc)
+
 _lib = None
 
 # every symbol include/pbrcuda.h declares (tests check that the built library exports all of them)
 EXPORTS = (
     "pbr_abi_version", "pbr_strerror", "pbr_ct_forward", "pbr_ct_backward", "pbr_ct_loss_fwd_bwd",
     "pbr_convert_m2s", "pbr_convert_s2m", "pbr_blend", "pbr_color_convert", "pbr_normal_min",
-    "pbr_normal_ingest", "pbr_launch_count",
+    "pbr_normal_ingest", "pbr_launch_count", "pbr_sizeof",
 )
 
 
@@ -118,6 +123,8 @@ def load():
     lib.pbr_strerror.restype = c_char_p
     lib.pbr_strerror.argtypes = [c_int]
     lib.pbr_launch_count.restype = c_uint64
+    lib.pbr_sizeof.restype = c_uint64
+    lib.pbr_sizeof.argtypes = [c_int]
     lib.pbr_ct_forward.argtypes = [POINTER(PbrCtDesc), c_void_p]
     lib.pbr_ct_backward.argtypes = [POINTER(PbrCtDesc), POINTER(PbrCtGrads), c_void_p]
     lib.pbr_ct_loss_fwd_bwd.argtypes = [POINTER(PbrCtDesc), POINTER(PbrCtLoss), POINTER(PbrCtGrads), c_void_p]
@@ -129,10 +136,13 @@ def load():
     lib.pbr_normal_ingest.argtypes = [POINTER(PbrNormalDesc), c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("pbr_strerror", "pbr_launch_count"):
+        if name not in ("pbr_strerror", "pbr_launch_count", "pbr_sizeof"):
             fn.restype = c_int
-    if lib.pbr_abi_version() != 1:
+    if lib.pbr_abi_version() != ABI_VERSION:
         raise ImportError(f"pypbr_b200: ABI version mismatch in {_LIB_PATH}")
+    for which, st in enumerate(STRUCTS):
+        if lib.pbr_sizeof(which) != ctypes.sizeof(st):
+            raise ImportError(f"pypbr_b200: layout of {st.__name__} differs between _cabi.py and {_LIB_PATH}")
     _lib = lib
     return lib
 

@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <climits>
+#include <cstdlib>
 
 #include "../../include/pbrcuda.h"
 #include "pbr_shade.cuh"
@@ -107,6 +109,7 @@ struct CtKParams {
   CtFlags flags;
   int vec_ok;
   int is_loss;           // backward: grad_out is derived from (render - target)
+  int force_generic;     // PbrCtDesc.force_generic
   PbrPlane albedo, normal, roughness, metspec, out;
   int64_t out_sl;
   // backward: `gsrc` is grad_out, or the target image when is_loss
@@ -360,6 +363,12 @@ __global__ void __launch_bounds__(kThreads, PBR_BWD_MIN_CTAS) ct_backward_kernel
   }
 }
 
+}  // namespace pbr
+
+#include "pbr_ct_stream.cuh"
+
+namespace pbr {
+
 // ------------------------------------------------------------------------------------------------
 // streaming kernels: workflow conversions, blend, colour space, normal ingestion
 // ------------------------------------------------------------------------------------------------
@@ -583,6 +592,7 @@ static int fill_ct_params(const PbrCtDesc* d, CtKParams& k) {
   if (d->light_type != PBR_LIGHT_DIRECTIONAL && d->light_type != PBR_LIGHT_POINT) return PBR_E_ENUM;
   if (!d->albedo.ptr || !d->roughness.ptr || !d->metspec.ptr || !d->view || !d->lights || !d->intensity) return PBR_E_NULL;
   k.B = d->B; k.H = d->H; k.W = d->W;
+  k.force_generic = d->force_generic;
   k.flags.L = d->L;
   k.flags.point = d->light_type == PBR_LIGHT_POINT;
   k.flags.albedo_is_srgb = d->albedo_is_srgb != 0;
@@ -659,6 +669,114 @@ static int fill_grads(const PbrCtGrads* g, CtKParams& k) {
   return PBR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// streamed (TMA-fed) fast path: one light, 16-byte aligned planes, W % 4 == 0 (pbr_ct_stream.cuh)
+// ------------------------------------------------------------------------------------------------
+static bool stream_disabled() {
+  static const bool off = [] { const char* e = getenv("PBR_DISABLE_STREAM"); return e && e[0] && e[0] != '0'; }();
+  return off;
+}
+
+static bool fits_i32(const PbrPlane& pl, int H, int W) {
+  return !pl.ptr || ((int64_t)(H - 1) * pl.sh + W) < (int64_t)INT32_MAX;
+}
+
+static bool stream_shape(const CtKParams& k, dim3& grid, dim3& block, int& mats) {
+  if (stream_disabled() || k.force_generic || k.flags.L != 1 || !k.vec_ok || (k.W % 4) != 0 || kTexels != 4) return false;
+  static const int min_bx = [] { const char* e = getenv("PBR_STREAM_MIN_BX"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
+  int groups = k.W / 4, bx = min_bx;
+  while (bx < groups && bx < kThreads) bx <<= 1;
+  int by = kThreads / bx;
+  int64_t gy = ((int64_t)k.H + by - 1) / by;
+  if (gy > 65535) return false;
+  mats = k.B < kHoistMats ? k.B : kHoistMats;
+  block = dim3(bx, by, 1);
+  grid = dim3((groups + bx - 1) / bx, (unsigned)gy, (k.B + mats - 1) / mats);
+  return true;
+}
+
+template <void (*Kern)(CtKParams)>
+static void stream_launch(const CtKParams& k, dim3 grid, dim3 block, int planes, cudaStream_t st) {
+  static std::atomic<uint64_t> configured{0};   // per kernel instantiation: bit d = opted in on device d
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(configured.load(std::memory_order_acquire) & bit)) {
+    cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSrcPlanes * kTileFloats * 4 * kStages);
+    configured.fetch_or(bit, std::memory_order_release);
+  }
+  size_t smem = (size_t)planes * kTileFloats * 4 * kStages;
+  Kern<<<grid, block, smem, st>>>(k);
+}
+
+template <int WF>
+static void launch_fwd_stream(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t st) {
+  const int planes = k.normal.ptr ? Slots<WF, false>::count : Slots<WF, false>::count_no_normal;
+  if (k.flags.point) stream_launch<ct_forward_stream<WF, kLightPointHoisted>>(k, grid, block, planes, st);
+  else stream_launch<ct_forward_stream<WF, kLightDirectional>>(k, grid, block, planes, st);
+}
+
+template <int WF, int kMode>
+static void launch_bwd_stream_m(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t st) {
+  const int planes = k.normal.ptr ? Slots<WF, true>::count : Slots<WF, true>::count_no_normal;
+  if (k.flags.point) stream_launch<ct_backward_stream<WF, kLightPointHoisted, kMode>>(k, grid, block, planes, st);
+  else stream_launch<ct_backward_stream<WF, kLightDirectional, kMode>>(k, grid, block, planes, st);
+}
+
+template <int WF>
+static void launch_bwd_stream(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t st) {
+  const int mode = (k.is_loss ? kModeLoss : 0) | (k.d_intensity ? kModeIntGrad : 0);
+  switch (mode) {
+    case 0: launch_bwd_stream_m<WF, 0>(k, grid, block, st); break;
+    case 1: launch_bwd_stream_m<WF, 1>(k, grid, block, st); break;
+    case 2: launch_bwd_stream_m<WF, 2>(k, grid, block, st); break;
+    default: launch_bwd_stream_m<WF, 3>(k, grid, block, st); break;
+  }
+}
+
+// shared tail of the three Cook-Torrance entry points
+static int ct_dispatch(CtKParams& k, int wf, bool backward, cudaStream_t st) {
+  dim3 grid, block;
+  int mats = 1;
+  bool stream = stream_shape(k, grid, block, mats);
+  if (stream) {
+    if (backward) stream = fits_i32(k.d_albedo, k.H, k.W) && fits_i32(k.d_normal, k.H, k.W) && fits_i32(k.d_roughness, k.H, k.W) && fits_i32(k.d_metspec, k.H, k.W);
+    else stream = fits_i32(k.out, k.H, k.W);
+  }
+  if (stream) {
+    k.mats_per_cta = mats;
+    if (backward) {
+      switch (wf) {
+        case 0: launch_bwd_stream<0>(k, grid, block, st); break;
+        case 1: launch_bwd_stream<1>(k, grid, block, st); break;
+        default: launch_bwd_stream<2>(k, grid, block, st); break;
+      }
+    } else {
+      switch (wf) {
+        case 0: launch_fwd_stream<0>(k, grid, block, st); break;
+        case 1: launch_fwd_stream<1>(k, grid, block, st); break;
+        default: launch_fwd_stream<2>(k, grid, block, st); break;
+      }
+    }
+    return launch_result();
+  }
+  ct_launch_shape(k, grid, block);
+  if (backward) {
+    switch (wf) {
+      case 0: launch_bwd<0>(k, grid, block, st); break;
+      case 1: launch_bwd<1>(k, grid, block, st); break;
+      default: launch_bwd<2>(k, grid, block, st); break;
+    }
+  } else {
+    switch (wf) {
+      case 0: launch_fwd<0>(k, grid, block, st); break;
+      case 1: launch_fwd<1>(k, grid, block, st); break;
+      default: launch_fwd<2>(k, grid, block, st); break;
+    }
+  }
+  return launch_result();
+}
+
 }  // namespace pbr
 
 using namespace pbr;
@@ -679,6 +797,21 @@ const char* pbr_strerror(int code) {
   }
 }
 
+uint64_t pbr_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(PbrPlane);
+    case 1: return sizeof(PbrCtDesc);
+    case 2: return sizeof(PbrCtGrads);
+    case 3: return sizeof(PbrCtLoss);
+    case 4: return sizeof(PbrConvDesc);
+    case 5: return sizeof(PbrBlendMap);
+    case 6: return sizeof(PbrBlendDesc);
+    case 7: return sizeof(PbrColorDesc);
+    case 8: return sizeof(PbrNormalDesc);
+    default: return 0;
+  }
+}
+
 uint64_t pbr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int pbr_ct_forward(const PbrCtDesc* desc, pbr_stream_t stream) {
@@ -686,14 +819,7 @@ int pbr_ct_forward(const PbrCtDesc* desc, pbr_stream_t stream) {
   if (int rc = fill_ct_params(desc, k)) return rc;
   if (!desc->out.ptr) return PBR_E_NULL;
   k.vec_ok = k.vec_ok && plane_vec_ok(desc->out) && (desc->out_sl % kTexels == 0);
-  dim3 grid, block;
-  ct_launch_shape(k, grid, block);
-  switch (kernel_workflow(desc)) {
-    case 0: launch_fwd<0>(k, grid, block, (cudaStream_t)stream); break;
-    case 1: launch_fwd<1>(k, grid, block, (cudaStream_t)stream); break;
-    default: launch_fwd<2>(k, grid, block, (cudaStream_t)stream); break;
-  }
-  return launch_result();
+  return ct_dispatch(k, kernel_workflow(desc), false, (cudaStream_t)stream);
 }
 
 int pbr_ct_backward(const PbrCtDesc* desc, const PbrCtGrads* grads, pbr_stream_t stream) {
@@ -704,14 +830,7 @@ int pbr_ct_backward(const PbrCtDesc* desc, const PbrCtGrads* grads, pbr_stream_t
   k.gsrc = grads->grad_out; k.gsrc_sl = grads->grad_out_sl;
   k.is_loss = 0;
   k.vec_ok = k.vec_ok && plane_vec_ok(grads->grad_out) && (grads->grad_out_sl % kTexels == 0);
-  dim3 grid, block;
-  ct_launch_shape(k, grid, block);
-  switch (kernel_workflow(desc)) {
-    case 0: launch_bwd<0>(k, grid, block, (cudaStream_t)stream); break;
-    case 1: launch_bwd<1>(k, grid, block, (cudaStream_t)stream); break;
-    default: launch_bwd<2>(k, grid, block, (cudaStream_t)stream); break;
-  }
-  return launch_result();
+  return ct_dispatch(k, kernel_workflow(desc), true, (cudaStream_t)stream);
 }
 
 int pbr_ct_loss_fwd_bwd(const PbrCtDesc* desc, const PbrCtLoss* loss, const PbrCtGrads* grads, pbr_stream_t stream) {
@@ -723,14 +842,7 @@ int pbr_ct_loss_fwd_bwd(const PbrCtDesc* desc, const PbrCtLoss* loss, const PbrC
   k.is_loss = 1;
   k.loss_scale = loss->loss_scale; k.loss_sum = loss->loss_sum;
   k.vec_ok = k.vec_ok && plane_vec_ok(loss->target) && (loss->target_sl % kTexels == 0);
-  dim3 grid, block;
-  ct_launch_shape(k, grid, block);
-  switch (kernel_workflow(desc)) {
-    case 0: launch_bwd<0>(k, grid, block, (cudaStream_t)stream); break;
-    case 1: launch_bwd<1>(k, grid, block, (cudaStream_t)stream); break;
-    default: launch_bwd<2>(k, grid, block, (cudaStream_t)stream); break;
-  }
-  return launch_result();
+  return ct_dispatch(k, kernel_workflow(desc), true, (cudaStream_t)stream);
 }
 
 static int run_convert(const PbrConvDesc* d, bool m2s, pbr_stream_t stream) {

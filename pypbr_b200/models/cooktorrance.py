@@ -28,6 +28,10 @@ from .. import _cabi
 from ..materials import MaterialBase
 
 
+# A/B switch for tests and tuning: True routes every call to the generic kernels (PbrCtDesc.force_generic).
+FORCE_GENERIC = False
+
+
 class BRDFModel(nn.Module, ABC):
     """Abstract base class for BRDF models."""
 
@@ -67,6 +71,7 @@ def _fill_desc(cfg: _ShadeCfg, albedo, normal, roughness, metspec, keep: list) -
     d.roughness = _cabi.plane(roughness)
     d.metspec = _cabi.plane(metspec)
     d.params_on_device = int(cfg.on_device)
+    d.force_generic = int(FORCE_GENERIC)
     if cfg.on_device:
         d.view, d.lights, d.intensity = cfg.view.data_ptr(), cfg.lights.data_ptr(), cfg.intensity.data_ptr()
     else:

@@ -14,6 +14,17 @@ pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0") if torch.cuda.is_available() else None
 
 
+@pytest.fixture(params=["auto", "generic"])
+def ct_path(request):
+    """Run a test once with the automatic kernel choice (streamed TMA-fed kernels where they apply) and once
+    pinned to the generic kernels (PbrCtDesc.force_generic)."""
+    from pypbr_b200.models import cooktorrance as ct
+
+    ct.FORCE_GENERIC = request.param == "generic"
+    yield request.param
+    ct.FORCE_GENERIC = False
+
+
 def _material(maps, p, requires_grad=False, device=None):
     from pypbr_b200.materials import BasecolorMetallicMaterial, DiffuseSpecularMaterial
 
@@ -39,7 +50,7 @@ def _brdf(p, per_light):
 
 
 @pytest.mark.parametrize("name", golden_ct_cases())
-def test_cooktorrance_golden_forward_backward(name):
+def test_cooktorrance_golden_forward_backward(name, ct_path):
     z = load_golden(name)
     maps, view, lights, inten, p, multi, per_light = case_inputs(z)
     mat, leaves = _material(maps, p, requires_grad=True)
@@ -109,8 +120,11 @@ def _random_case(seed, B, H, W, L, workflow="metallic", rough_lo=0.2, normal=Tru
     (2, 24, 36, 3, False, "specular"),    # per-light outputs
     (None, 1, 1, 1, True, "metallic"),    # degenerate 1x1 (linspace of one step)
     (2, 3, 1030, 1, True, "metallic"),    # wider than one CTA row
+    (19, 9, 256, 1, True, "metallic"),    # streamed path: 4 rows per tile, H % 4 != 0, B > one CTA's walk
+    (2, 2, 1536, 1, True, "specular"),    # streamed path: second strip half empty
+    (3, 5, 72, 1, False, "metallic"),     # streamed path: per_light flag with a single light, narrow image
 ])
-def test_against_oracle_seeded(B, H, W, L, acc, wf):
+def test_against_oracle_seeded(B, H, W, L, acc, wf, ct_path):
     """Fresh seeded inputs (not in the fixtures) against the oracle run on the host."""
     from oracle import pbr_oracle as O
 
@@ -379,3 +393,47 @@ def test_native_library_is_the_code_path():
     before = _cabi.launch_count()
     CookTorranceBRDF("point")(mat, torch.tensor([0.0, 0.0, 1.0]), lights, inten)
     assert _cabi.launch_count() == before + 1
+
+
+@pytest.mark.parametrize("light_type", ["point", "directional"])
+@pytest.mark.parametrize("wf,normal", [("metallic", True), ("metallic", False), ("specular", True)])
+def test_streamed_kernels_equal_generic_kernels(light_type, wf, normal):
+    """The streamed (TMA-fed) and the generic kernels run the same per-texel code; the compiler may contract
+    multiply-adds of the tolerant zone differently in the two instantiations, so they must agree to a few ulp
+    (far inside the parity tolerance); the fused loss / intensity reductions also differ in summation order."""
+    from pypbr_b200.fit import fused_loss_step
+    from pypbr_b200.models import CookTorranceBRDF
+    from pypbr_b200.models import cooktorrance as ct
+
+    maps, lights, inten, g = _random_case(31, 21, 12, 520, 1, wf, normal=normal)
+    if light_type == "directional":
+        lights = torch.tensor([0.2, -0.3, 0.9])
+    view = torch.tensor([0.1, 0.0, 1.0])
+    p = dict(light_type=light_type)
+    res = {}
+    for path in ("auto", "generic"):
+        ct.FORCE_GENERIC = path == "generic"
+        try:
+            mat, leaves = _material(maps, p, requires_grad=True)
+            it = inten.clone().to(DEV).requires_grad_(True)
+            out = CookTorranceBRDF(light_type)(mat, view, lights, it, 1.0)
+            go = torch.rand(out.shape, generator=torch.Generator().manual_seed(3)).to(DEV)
+            out.backward(go)
+            tgt = torch.rand(out.shape, generator=torch.Generator().manual_seed(4)).to(DEV)
+            buf, grads = fused_loss_step(mat, tgt, view, lights, inten, light_type, 1.0, want_intensity_grad=True)
+            res[path] = (out.detach().clone(), {k: v.grad.clone() for k, v in leaves.items()}, it.grad.clone(),
+                         buf.clone(), {k: v.clone() for k, v in grads.items() if v is not None})
+        finally:
+            ct.FORCE_GENERIC = False
+    a, b = res["auto"], res["generic"]
+
+    def close(x, y, rtol):
+        return bool(((x - y).abs() <= rtol * y.abs() + rtol * y.abs().mean()).all())
+
+    assert close(a[0], b[0], 2e-6)
+    for k in a[1]:
+        assert close(a[1][k], b[1][k], 1e-5), k
+    assert torch.allclose(a[2], b[2], rtol=1e-4, atol=1e-6)
+    assert torch.allclose(a[3], b[3], rtol=1e-4, atol=1e-6)
+    for k in a[4]:
+        assert close(a[4][k], b[4][k], 1e-5), k

@@ -25,15 +25,20 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_cabi.lib_path())
     for name in declared:
         assert hasattr(lib, name), name
-    assert _cabi.load().pbr_abi_version() == 1
+    assert _cabi.load().pbr_abi_version() == _cabi.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header_sizes():
     # sizes the C compiler produces for the same declarations (LP64): catches field-order drift
     assert ctypes.sizeof(_cabi.PbrPlane) == 32
-    assert ctypes.sizeof(_cabi.PbrCtDesc) == 12 * 4 + 4 * 32 + 8 + 3 * 8 + 32 + 8
+    assert ctypes.sizeof(_cabi.PbrCtDesc) == 12 * 4 + 4 * 32 + 8 + 3 * 8 + 32 + 8 + 8
     assert ctypes.sizeof(_cabi.PbrCtGrads) == 32 + 8 + 4 * 32 + 8
     assert ctypes.sizeof(_cabi.PbrBlendMap) == 3 * 32 + 8
+    # ... and against the sizes the library itself reports (pbr_sizeof), for every descriptor
+    lib = _cabi.load()
+    for which, st in enumerate(_cabi.STRUCTS):
+        assert lib.pbr_sizeof(which) == ctypes.sizeof(st), st.__name__
+    assert lib.pbr_sizeof(99) == 0
 
 
 def test_argument_errors_come_back_as_codes_without_touching_the_gpu():

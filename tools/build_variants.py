@@ -1,4 +1,5 @@
-"""Build tuning variants of libpbrcuda.so (different -D knobs) into pypbr_b200/lib/variants/ — run on the CPU box."""
+"""Build tuning variants of libpbrcuda.so (different -D knobs) into pypbr_b200/lib/variants/ — run on the CPU box.
+usage: python tools/build_variants.py [name ...]   (default: all)"""
 import os
 import sys
 from concurrent.futures import ThreadPoolExecutor
@@ -7,28 +8,28 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as g  # noqa: E402
 
-def v(texels, fg, bg, fcta, bcta, hoist=8, threads=256):
-    return [f"-DPBR_TEXELS={texels}", f"-DPBR_FWD_GROUP={fg}", f"-DPBR_BWD_GROUP={bg}", f"-DPBR_FWD_MIN_CTAS={fcta}",
-            f"-DPBR_BWD_MIN_CTAS={bcta}", f"-DPBR_HOIST_MATS={hoist}", f"-DPBR_THREADS={threads}"]
+
+def v(**kw):
+    return [f"-DPBR_{k.upper()}={val}" for k, val in kw.items()]
 
 
 VARIANTS = {
-    "strict": v(4, 2, 1, 3, 2) + ["-DPBR_STRICT_IEEE"],
-    "t4_f2c3_b1c2": v(4, 2, 1, 3, 2),
-    "t4_f2c3_b1c2_h16": v(4, 2, 1, 3, 2, hoist=16),
-    "t4_f1c4_b1c3": v(4, 1, 1, 4, 3),
-    "t2_f2c4_b1c2": v(2, 2, 1, 4, 2),
-    "t2_f2c4_b1c3": v(2, 2, 1, 4, 3),
-    "t2_f1c5_b1c3": v(2, 1, 1, 5, 3),
-    "t1_c3_c2": v(1, 1, 1, 3, 2),
-    "t1_c4_c2": v(1, 1, 1, 4, 2),
-    "t1_c4_c3": v(1, 1, 1, 4, 3),
-    "t1_c5_c3": v(1, 1, 1, 5, 3),
-    "t1_c6_c4": v(1, 1, 1, 6, 4),
-    "t1_c4_c3_h16": v(1, 1, 1, 4, 3, hoist=16),
-    "t1_c4_c3_h4": v(1, 1, 1, 4, 3, hoist=4),
-    "t1_128_c8_c6": v(1, 1, 1, 8, 6, threads=128),
-    "t2_128_c8_c5": v(2, 2, 1, 8, 5, threads=128),
+    "strict": ["-DPBR_STRICT_IEEE"],
+    "default": [],
+    # streamed kernels: stages / CTAs per SM (register cap) / texels shaded together / materials per CTA walk
+    "f2g2": v(stream_fwd_min_ctas=2),
+    "f2g4": v(stream_fwd_min_ctas=2, stream_fwd_group=4),
+    "f3g1": v(stream_fwd_group=1),
+    "f4g1": v(stream_fwd_min_ctas=4, stream_fwd_group=1),
+    "f2g2_s3": v(stream_fwd_min_ctas=2, stream_stages=3),
+    "b2g2": v(stream_bwd_group=2),
+    "b3g1": v(stream_bwd_min_ctas=3),
+    "h8": v(hoist_mats=8),
+    "h32": v(hoist_mats=32),
+    "h64": v(hoist_mats=64),
+    "t128_f6b4": v(threads=128, stream_fwd_min_ctas=6, stream_bwd_min_ctas=4),
+    "t128_f4b4_s3": v(threads=128, stream_fwd_min_ctas=4, stream_bwd_min_ctas=4, stream_stages=3),
+    "t512_f1b1": v(threads=512, stream_fwd_min_ctas=1, stream_bwd_min_ctas=1),
 }
 
 
