@@ -2,7 +2,7 @@
 """
 bench.py — CookTorrance forward+backward throughput (BASELINE.json metric), one JSON line on stdout.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c5]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c5]
 
 Workload (N=1): BASELINE.json configs[1] — batch 64 materials 1024x1024, CookTorrance forward+backward,
 1 point light, fp32, metallic workflow, sRGB albedo in / sRGB colour out.  A step = one forward pass
@@ -46,6 +46,8 @@ CONFIGS = {
     "c5": dict(B=512, H=512, W=512, L=8, per_light=True,
                workload="SVBRDF fit step, 512 materials 512x512 per GPU, 8 lights, fused loss forward+backward"),
 }
+C4 = dict(H=4096, W=4096,
+          workload="4096x4096 metallic->diffuse-specular conversion + mask/height blend_materials pipeline")
 FWD_BYTES, BWD_BYTES = 44, 76  # algorithmic bytes per texel, metallic workflow, accumulate mode
 
 
@@ -376,16 +378,156 @@ def run_ours(args, cfg):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------- config 4
+def run_c4(args):
+    """
+    BASELINE.json configs[3] (SURVEY.md §8d "C4"): two 4096x4096 metallic materials (albedo, normal, roughness,
+    metallic, height) -> to_diffuse_specular_material() on each -> blend_materials(d1, d2, "mask", mask) ->
+    blend_materials(m1, m2, "height").  Two measurements:
+      pipeline : the four public-API calls back to back (host allocation, the normal-min probes and their 4-byte
+                 readbacks included), CUDA-event time per pipeline
+      kernels  : every kernel on its own through the C ABI on preallocated buffers (launches back to back between
+                 two CUDA events), algorithmic bytes / time against the measured HBM peak
+    """
+    from pypbr_b200 import _cabi
+    from pypbr_b200.blending import blend_materials
+    from pypbr_b200.materials import BasecolorMetallicMaterial
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the conversion / blend path has no CPU fallback)")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    lib = _cabi.load()
+    H, W = C4["H"], C4["W"]
+    texels = H * W
+    peak, peak_src = measured_peak()
+    st = _cabi.stream_ptr(dev)
+
+    def material(seed):
+        m = synth_maps(1, H, W, dev, seed)
+        g = torch.Generator(device=dev).manual_seed(seed + 50)
+        mat = BasecolorMetallicMaterial(albedo_is_srgb=True, device=dev)
+        for k, v in m.items():
+            mat._maps[k] = v[0]
+        mat._maps["height"] = torch.rand(1, H, W, generator=g, device=dev)
+        return mat
+
+    m1, m2 = material(4001), material(4002)
+    mask = torch.rand(1, H, W, generator=torch.Generator(device=dev).manual_seed(4003), device=dev)
+
+    def pipeline():
+        d1 = m1.to_diffuse_specular_material()
+        d2 = m2.to_diffuse_specular_material()
+        b1, _ = blend_materials(d1, d2, "mask", mask=mask)
+        b2, mk = blend_materials(m1, m2, "height", blend_width=0.1)
+        return b1, b2, mk
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for _ in range(max(args.warmup, 3)):
+        pipeline()
+    torch.cuda.synchronize()
+    l0 = _cabi.launch_count()
+    e0, e1 = ev(), ev()
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            pipeline()
+        e1.record()
+        torch.cuda.synchronize()
+    launches = _cabi.launch_count() - l0
+    pipe_ms = e0.elapsed_time(e1) / args.steps
+
+    # kernel-only legs through the C ABI
+    d1 = m1.to_diffuse_specular_material()
+    d2 = m2.to_diffuse_specular_material()
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    kernels = {}
+
+    def add(name, ms, bytes_per_texel):
+        ach = bytes_per_texel * texels / (ms * 1e-3) / 1e9
+        kernels[name] = {"ms": ms, "bytes_per_texel": bytes_per_texel, "achieved": ach, "frac": ach / peak}
+
+    o0, o1 = torch.empty(3, H, W, device=dev), torch.empty(3, H, W, device=dev)
+    cd = _cabi.PbrConvDesc(1, H, W, 1, _cabi.plane(m1.albedo), _cabi.plane(m1.metallic), _cabi.plane(o0), _cabi.plane(o1))
+    add("convert_m2s (K4)", timed(lambda: _cabi.check(lib.pbr_convert_m2s(_cabi.byref(cd), st), "m2s")), 16 + 24)
+    cs = _cabi.PbrConvDesc(1, H, W, 0, _cabi.plane(d1.albedo), _cabi.plane(d1.specular), _cabi.plane(o0), _cabi.plane(o1))
+    add("convert_s2m (K5)", timed(lambda: _cabi.check(lib.pbr_convert_s2m(_cabi.byref(cs), st), "s2m")), 24 + 24)
+    res = torch.full((1,), float("inf"), device=dev)
+    nd = _cabi.PbrNormalDesc(1, H, W, 3, _cabi.plane(m1.normal), _cabi.plane(None))
+    add("normal_min probe (K7)", timed(lambda: _cabi.check(lib.pbr_normal_min(_cabi.byref(nd), res.data_ptr(), st), "nmin")), 12)
+
+    def blend_desc(a, b, names, mode):
+        d = _cabi.PbrBlendDesc()
+        d.B, d.H, d.W, d.mask_mode = 1, H, W, mode
+        d.blend_width, d.shift, d.apply_shift = 0.1, 0.0, 1
+        outs, ch_total = [], 0
+        for i, n in enumerate(names):
+            ta, tb = a._maps[n], b._maps[n]
+            out = torch.empty_like(ta)
+            outs.append(out)
+            d.maps[i] = _cabi.PbrBlendMap(_cabi.plane(ta), _cabi.plane(tb), _cabi.plane(out), ta.shape[0], int(n == "normal"))
+            ch_total += ta.shape[0]
+        d.n_maps = len(names)
+        d.normal_min = res.data_ptr()
+        return d, outs, ch_total
+
+    bd, keep1, ch = blend_desc(d1, d2, ["albedo", "normal", "roughness", "specular"], _cabi.MASK_GIVEN)
+    bd.mask = _cabi.plane(mask)
+    add("blend, given mask, diffuse-specular pair (K6)", timed(lambda: _cabi.check(lib.pbr_blend(_cabi.byref(bd), st), "blend")),
+        4 * (2 * ch + 1) + 4 * ch)
+    bh, keep2, ch2 = blend_desc(m1, m2, ["albedo", "height", "metallic", "normal", "roughness"], _cabi.MASK_SIGMOID)
+    mask_out = torch.empty(1, H, W, device=dev)
+    bh.prop1, bh.prop2, bh.mask_out = _cabi.plane(m1.height), _cabi.plane(m2.height), _cabi.plane(mask_out)
+    # the two height planes are read twice by one thread (mask builder + the height map's own lerp): second read is L1/L2
+    add("blend, height sigmoid, metallic pair (K6)", timed(lambda: _cabi.check(lib.pbr_blend(_cabi.byref(bh), st), "blend")),
+        4 * (2 * ch2) + 4 * ch2 + 4)
+
+    total_bytes = texels * (2 * (40 + 12) + kernels["blend, given mask, diffuse-specular pair (K6)"]["bytes_per_texel"] + 12
+                            + kernels["blend, height sigmoid, metallic pair (K6)"]["bytes_per_texel"] + 12)
+    dom = max(kernels.items(), key=lambda kv: kv[1]["ms"])
+    line = {
+        "metric": "Gtexel/s conversion + blend pipeline", "value": texels / (pipe_ms * 1e-3) / 1e9, "unit": "Gtexel/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": pipe_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": C4["workload"], "H": H, "W": W,
+                   "pipeline": "2 x to_diffuse_specular_material + blend_materials(mask) + blend_materials(height), public API",
+                   "l2": "every kernel streams 0.6-2 GB, far above the 126 MB L2; no flush needed"},
+        "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": dom[1]["achieved"], "peak": peak, "unit": "GB/s",
+                     "frac": dom[1]["frac"], "traffic": None, "peak_source": peak_src,
+                     "pipeline_algorithmic_bytes": total_bytes,
+                     "pipeline_frac": total_bytes / (pipe_ms * 1e-3) / 1e9 / peak, "kernels": kernels},
+        "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clk.summary(),
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="c2", choices=sorted(list(CONFIGS) + ["c4"]))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.config == "c4":
+        if args.impl == "reference":
+            raise SystemExit("bench.py: the reference arm is defined for the shading configs (c2/c3/c5) only")
+        return run_c4(args)
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
         run_reference_arm(args, cfg)

@@ -2,6 +2,7 @@
 // mbarrier (transaction-count completion) + cp.async.bulk (the TMA engine's 1-D bulk copy,
 // global -> shared).  A row segment of one channel plane is one contiguous run of bytes, so no
 // tensor map is needed; every copy is >= 16 B, 16-byte aligned on both sides.
+// (A shared -> global bulk-store epilogue was measured and dropped: profiles/r1_ncu_summary.md.)
 #pragma once
 
 #include <cuda_runtime.h>

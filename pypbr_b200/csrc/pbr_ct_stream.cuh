@@ -7,20 +7,29 @@
 // allows (ncu: 24 % warps active, 64 % issue-slot use, 55 % of HBM peak for the generic backward).
 // Here the copy engine does the loading:
 //
-//   tile    = blockDim.y rows x (blockDim.x * 4) texels of ONE material: every input plane of the tile
+//   tile    = blockDim.y rows x (blockDim.x * kST) texels of ONE material: every input plane of the tile
 //             (albedo x3, roughness, metallic | specular, normal x3, and grad_out | target x3 for the
-//             backward) is kTileFloats contiguous floats of shared memory per stage;
+//             backward) is kTileFloats contiguous floats of shared memory per stage, in image order;
 //   producer= warp 0: one cp.async.bulk per (plane, row) -> stage buffer, completion counted in bytes
 //             on the stage's mbarrier (pbr_async.cuh);
-//   consumer= all threads: wait for the stage, pull their 4 texels of every plane into registers with
-//             LDS.128 at immediate offsets, one arrival per warp on the stage's "empty" mbarrier, shade
-//             from registers, write results with STG.128; warp 0 then waits for "empty" (already
-//             complete in practice) and refills the stage with the tile that is kStages ahead.
-//             There is no CTA-wide barrier inside the loop.
+//   consumer= all threads.  A thread owns kSSlots lane-values (texel pairs) of one tile row, INTERLEAVED
+//             with the other threads of the row: slot j of thread tx covers the texels
+//             j*(bx*kLanes) + tx*kLanes ... + kLanes-1 of the row.  So one warp-level LDS.64 / STG.64
+//             touches 256 contiguous bytes: no shared-memory bank conflicts, full 32-byte sectors on
+//             the way out.  The forward kernel shades all of a thread's slots together (ILP); the
+//             backward takes them one at a time - inputs come out of the stage right before they are
+//             used and the gradients leave right after, so only one pair's working set is live in
+//             registers (the adjoint needs ~170 of them).  After its last read of a stage a warp
+//             arrives once on the stage's "empty" mbarrier; warp 0 waits for it (complete in practice)
+//             and refills the stage with the tile that is kStages ahead.  No CTA-wide barrier in the loop.
 //
 // A CTA walks over `mats_per_cta` materials at a fixed image position, so for a point light the
 // per-texel light geometry (material independent) is computed once and reused - as in the generic
 // kernels - and the pipeline stays full for the whole walk.
+//
+// Measured floor of this data-movement design with the shading math compiled out (-DPBR_DBG_NOMATH,
+// tools/build_variants.py): 6.4-6.5 TB/s forward and backward, i.e. 98-99 % of the measured copy peak;
+// whatever the real kernels lose against that is instruction issue, not memory.
 #pragma once
 
 #include "pbr_async.cuh"
@@ -30,22 +39,25 @@ namespace pbr {
 #ifndef PBR_STREAM_STAGES
 #define PBR_STREAM_STAGES 2
 #endif
+#ifndef PBR_STREAM_THREADS
+#define PBR_STREAM_THREADS 128
+#endif
+#ifndef PBR_STREAM_TEXELS
+#define PBR_STREAM_TEXELS 4   // texels per thread: 4 (two packed pairs) or 2 (one pair)
+#endif
 #ifndef PBR_STREAM_FWD_MIN_CTAS
-#define PBR_STREAM_FWD_MIN_CTAS 2
+#define PBR_STREAM_FWD_MIN_CTAS 4   // 128 registers
 #endif
 #ifndef PBR_STREAM_BWD_MIN_CTAS
-#define PBR_STREAM_BWD_MIN_CTAS 2
+#define PBR_STREAM_BWD_MIN_CTAS 3   // 168 registers
 #endif
-#ifndef PBR_STREAM_FWD_GROUP
-#define PBR_STREAM_FWD_GROUP 4
-#endif
-#ifndef PBR_STREAM_BWD_GROUP
-#define PBR_STREAM_BWD_GROUP 1
-#endif
-
+constexpr int kStreamThreads = PBR_STREAM_THREADS;
 constexpr int kStages = PBR_STREAM_STAGES;
-constexpr int kTileFloats = kThreads * 4;   // floats of one plane in one stage (4 KB at 256 threads)
-constexpr int kMaxSrcPlanes = 13;           // albedo 3 + roughness 1 + metallic|specular 3 + normal 3 + grad_out|target 3
+constexpr int kST = PBR_STREAM_TEXELS;
+static_assert((kST == 2 || kST == 4) && kST % kLanes == 0, "stream kernels: 2 or 4 texels per thread");
+constexpr int kSSlots = kST / kLanes;               // lane-values per thread
+constexpr int kTileFloats = kStreamThreads * kST;   // floats of one plane in one stage (2 KB at 128 threads x 4 texels)
+constexpr int kMaxSrcPlanes = 13;                   // albedo 3 + roughness 1 + metallic|specular 3 + normal 3 + grad_out|target 3
 
 // backward flavours (compile-time, so the plain backward carries no reduction code)
 constexpr int kModeLoss = 1;      // gsrc is the target image: grad_out = 2*scale*(render - target), loss reduced
@@ -60,7 +72,7 @@ struct StreamSrc {
 
 struct StreamShared {
   uint64_t full[kStages];    // producer -> consumers: the copies of the stage have landed (transaction bytes)
-  uint64_t empty[kStages];   // consumers -> producer: one arrival per warp once its threads hold the stage in registers
+  uint64_t empty[kStages];   // consumers -> producer: one arrival per warp after its last read of the stage
   StreamSrc src[kMaxSrcPlanes];
   int n_src;
 };
@@ -112,48 +124,65 @@ __device__ __forceinline__ void stream_issue(const StreamShared& sh, uint64_t* b
   }
 }
 
-__device__ __forceinline__ void lds4(const float* p, float (&dst)[4]) {
-  float4 v = *reinterpret_cast<const float4*>(p);
-  dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+// one lane-value (kLanes consecutive floats) from shared memory / to global memory
+__device__ __forceinline__ V lds_v(const float* p) {
+#if defined(PBR_SCALAR_LANES)
+  return *p;
+#else
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  return V{v.x, v.y};
+#endif
 }
-__device__ __forceinline__ void stg4(float* p, const float (&src)[4]) {
-  __stcs(reinterpret_cast<float4*>(p), make_float4(src[0], src[1], src[2], src[3]));
-}
-__device__ __forceinline__ float* plane_at(const PbrPlane& pl, int b, int c, int toff) {
-  return pl.ptr + ((int64_t)b * pl.sb + (int64_t)c * pl.sc) + toff;
+__device__ __forceinline__ void stg_v(float* p, V v) {
+#if defined(PBR_SCALAR_LANES)
+  __stcs(p, v);
+#else
+  __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+#endif
 }
 
 // Geometry of the tile this CTA owns and of the thread inside it.
 struct StreamWhere {
   int row0, col0;       // tile origin
-  int row, col;         // this thread's first texel
+  int row, col;         // this thread's row and the first texel of its slot 0
+  int slot_stride;      // texels between a thread's consecutive slots (= blockDim.x * kLanes)
+  int toff;             // offset of slot 0 inside a tile plane (floats)
   int rows_valid, seg_bytes, row_floats;
-  bool active;
+  bool row_ok;
 };
 __device__ __forceinline__ StreamWhere stream_locate(int H, int W) {
   StreamWhere w;
-  w.row_floats = blockDim.x * 4;
+  w.row_floats = blockDim.x * kST;
+  w.slot_stride = blockDim.x * kLanes;
   w.row0 = blockIdx.y * blockDim.y;
   w.col0 = blockIdx.x * w.row_floats;
   w.row = w.row0 + threadIdx.y;
-  w.col = w.col0 + threadIdx.x * 4;
+  w.col = w.col0 + threadIdx.x * kLanes;
+  w.toff = threadIdx.y * w.row_floats + threadIdx.x * kLanes;
   w.rows_valid = min((int)blockDim.y, H - w.row0);
   w.seg_bytes = min(w.row_floats, W - w.col0) * 4;
-  w.active = w.row < H && w.col < W;   // W % 4 == 0: a thread's 4 texels are all inside or all outside
+  w.row_ok = w.row < H;
   return w;
 }
+// W % 4 == 0 (and kLanes <= 2): a slot's texels are all inside or all outside the image
+__device__ __forceinline__ bool slot_active(const StreamWhere& w, int j, int W) { return w.row_ok && w.col + j * w.slot_stride < W; }
 
 template <int kLight>
-__device__ __forceinline__ void stream_coords(const CtStage& S, const StreamWhere& w, float (&x)[4], float& y,
-                                              LightGeom (&hg)[4]) {
-  const int row = w.active ? w.row : 0, col = w.active ? w.col : 0;
+__device__ __forceinline__ void stream_coords(const CtStage& S, const StreamWhere& w, int W, V (&x)[kSSlots], float& y,
+                                              LightGeomT<V> (&hg)[kSSlots]) {
+  const int row = w.row_ok ? w.row : 0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) x[i] = linspace_at(S.lsx, col + i);
+  for (int j = 0; j < kSSlots; ++j)
+#pragma unroll
+    for (int k = 0; k < kLanes; ++k) {
+      const int col = w.col + j * w.slot_stride + k;
+      lane_set(x[j], k, linspace_at(S.lsx, col < W ? col : W - 1));
+    }
   y = linspace_at(S.lsy, row);
   if (kLight == kLightPointHoisted) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      point_light_geom(S.light[0].p[0], S.light[0].p[1], S.light[0].p[2], x[i], y, S.vx, S.vy, S.vz, hg[i]);
+    for (int j = 0; j < kSSlots; ++j)
+      point_light_geom(S.light[0].p[0], S.light[0].p[1], S.light[0].p[2], x[j], y, S.vx, S.vy, S.vz, hg[j]);
   }
 }
 
@@ -161,9 +190,9 @@ __device__ __forceinline__ void stream_coords(const CtStage& S, const StreamWher
 // forward
 // ------------------------------------------------------------------------------------------------
 template <int WF, int kLight>
-__global__ void __launch_bounds__(kThreads, PBR_STREAM_FWD_MIN_CTAS) ct_forward_stream(const __grid_constant__ CtKParams p) {
+__global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_FWD_MIN_CTAS) ct_forward_stream(const __grid_constant__ CtKParams p) {
   using SL = Slots<WF, false>;
-  constexpr int G = PBR_STREAM_FWD_GROUP;
+  constexpr int G = kSSlots;   // all of the thread's pairs are shaded together
   extern __shared__ __align__(128) float stream_smem[];
   __shared__ CtStage S;
   __shared__ StreamShared sh;
@@ -172,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, PBR_STREAM_FWD_MIN_CTAS) ct_forward_
   if (tid == 0) {
     stream_build_table<WF, false>(p, w.row0, w.col0, sh);
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], kThreads / 32); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], kStreamThreads / 32); }
     mbar_init_fence();
   }
   stage_params(p, S);  // ends with __syncthreads()
@@ -187,57 +216,63 @@ __global__ void __launch_bounds__(kThreads, PBR_STREAM_FWD_MIN_CTAS) ct_forward_
       stream_issue(sh, &sh.full[k], stream_smem + k * stage_floats, b0 + k, w.rows_valid, w.seg_bytes, w.row_floats, policy);
   }
 
-  float x[4], y;
-  LightGeom hg[4];
-  stream_coords<kLight>(S, w, x, y, hg);
-  const int toff = w.row * (int)p.out.sh + w.col;
+  V x[kSSlots];
+  float y;
+  LightGeomT<V> hg[kSSlots];
+  stream_coords<kLight>(S, w, p.W, x, y, hg);
   const bool has_normal = p.normal.ptr != nullptr;
+  bool act[kSSlots];
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < kSSlots; ++j) { act[j] = slot_active(w, j, p.W); any = any || act[j]; }
+  // output pointer of material b0 at slot 0; advanced by one batch stride per tile (strides sit in the
+  // __grid_constant__ parameter block, i.e. the constant bank)
+  float* o = p.out.ptr + ((int64_t)b0 * p.out.sb + (int64_t)w.row * p.out.sh + w.col);
 
   for (int k = 0; k < ntiles; ++k) {
     const int s = k % kStages;
-    const float* st = stream_smem + s * stage_floats + tid * 4;
+    const float* st = stream_smem + s * stage_floats + w.toff;
     mbar_wait(&sh.full[s], (k / kStages) & 1);
-    float araw[3][4], nraw[3][4], rough[4], mraw[3][4];
+    V a[3][G], n[3][G], r[G], m[3][G];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) lds4(st + (SL::albedo + c) * kTileFloats, araw[c]);
-    lds4(st + SL::rough * kTileFloats, rough);
+    for (int j = 0; j < G; ++j) {
+      const float* sj = st + j * w.slot_stride;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      if (c < SL::mc) lds4(st + (SL::met + c) * kTileFloats, mraw[c]);
-      else mraw[c][0] = mraw[c][1] = mraw[c][2] = mraw[c][3] = 0.0f;
-    }
-    if (has_normal) {
+      for (int c = 0; c < 3; ++c) a[c][j] = lds_v(sj + (SL::albedo + c) * kTileFloats);
+      r[j] = lds_v(sj + SL::rough * kTileFloats);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) lds4(st + (SL::normal + c) * kTileFloats, nraw[c]);
-    } else {
+      for (int c = 0; c < 3; ++c) m[c][j] = c < SL::mc ? lds_v(sj + (SL::met + c) * kTileFloats) : splat<V>(0.0f);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { nraw[0][i] = 0.0f; nraw[1][i] = 0.0f; nraw[2][i] = 1.0f; }
+      for (int c = 0; c < 3; ++c) n[c][j] = has_normal ? lds_v(sj + (SL::normal + c) * kTileFloats) : splat<V>(c == 2 ? 1.0f : 0.0f);
     }
     // this warp holds its texels in registers: tell the producer (no CTA-wide barrier - warps drift freely)
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&sh.empty[s]);
-    if (w.active) {
-
-    const int b = b0 + k;
-    float outv[3][4];
-#pragma unroll
-    for (int g0 = 0; g0 < 4; g0 += G) {
-      float a[3][G], n[3][G], r[G], m[3][G], xs[G];
-      LightGeom hgs[G];
-      slice3<G>(araw, g0, a); slice3<G>(nraw, g0, n); slice3<G>(mraw, g0, m);
-#pragma unroll
-      for (int i = 0; i < G; ++i) { r[i] = rough[g0 + i]; xs[i] = x[g0 + i]; hgs[i] = hg[g0 + i]; }
-      auto emit = [&](int, const float(&v)[3][G]) {
+    if (any) {
+      V outv[3][G];
+      auto emit = [&](int, const V(&v)[3][G]) {
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
-          for (int i = 0; i < G; ++i) outv[c][g0 + i] = v[c][i];
+          for (int j = 0; j < G; ++j) outv[c][j] = v[c][j];
       };
-      ct_forward_group<WF, kLight, G>(S, p.flags, a, n, r, m, xs, y, hgs, emit);
-    }
+#if defined(PBR_DBG_NOMATH)   // memory pipeline only (tools/build_variants.py "nomath"): results are meaningless
 #pragma unroll
-    for (int c = 0; c < 3; ++c) stg4(plane_at(p.out, b, c, toff), outv[c]);
+      for (int j = 0; j < G; ++j)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) outv[c][j] = a[c][j] + n[c][j] + m[c][j] * r[j] + hg[j].lx + x[j];
+      (void)emit;
+#else
+      ct_forward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, x, y, hg, emit);
+#endif
+#pragma unroll
+      for (int j = 0; j < G; ++j)
+        if (act[j]) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) stg_v(o + c * p.out.sc + j * w.slot_stride, outv[c][j]);
+        }
     }
+    o += p.out.sb;
     // producer: by the time warp 0 has shaded tile k every warp has long since read stage s
     if (tid < 32 && k + kStages < ntiles) {
       mbar_wait(&sh.empty[s], (k / kStages) & 1);
@@ -251,21 +286,20 @@ __global__ void __launch_bounds__(kThreads, PBR_STREAM_FWD_MIN_CTAS) ct_forward_
 // backward / fused loss
 // ------------------------------------------------------------------------------------------------
 template <int WF, int kLight, int kMode>
-__global__ void __launch_bounds__(kThreads, PBR_STREAM_BWD_MIN_CTAS) ct_backward_stream(const __grid_constant__ CtKParams p) {
+__global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_backward_stream(const __grid_constant__ CtKParams p) {
   using SL = Slots<WF, true>;
-  constexpr int G = PBR_STREAM_BWD_GROUP;
   constexpr bool kLoss = (kMode & kModeLoss) != 0;
   constexpr bool kIntGrad = (kMode & kModeIntGrad) != 0;
   extern __shared__ __align__(128) float stream_smem[];
   __shared__ CtStage S;
   __shared__ StreamShared sh;
-  __shared__ float s_red[kThreads / 32][4];
+  __shared__ float s_red[kStreamThreads / 32][4];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const StreamWhere w = stream_locate(p.H, p.W);
   if (tid == 0) {
     stream_build_table<WF, true>(p, w.row0, w.col0, sh);
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], kThreads / 32); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], kStreamThreads / 32); }
     mbar_init_fence();
   }
   stage_params(p, S);  // ends with __syncthreads()
@@ -280,95 +314,91 @@ __global__ void __launch_bounds__(kThreads, PBR_STREAM_BWD_MIN_CTAS) ct_backward
       stream_issue(sh, &sh.full[k], stream_smem + k * stage_floats, b0 + k, w.rows_valid, w.seg_bytes, w.row_floats, policy);
   }
 
-  float x[4], y;
-  LightGeom hg[4];
-  stream_coords<kLight>(S, w, x, y, hg);
-  const int off_a = w.row * (int)p.d_albedo.sh + w.col;
-  const int off_n = w.row * (int)p.d_normal.sh + w.col;
-  const int off_r = w.row * (int)p.d_roughness.sh + w.col;
-  const int off_m = w.row * (int)p.d_metspec.sh + w.col;
+  V x[kSSlots];
+  float y;
+  LightGeomT<V> hg[kSSlots];
+  stream_coords<kLight>(S, w, p.W, x, y, hg);
   const bool has_normal = p.normal.ptr != nullptr;
-  float loss_local = 0.0f, gi_local[3] = {0.0f, 0.0f, 0.0f};
+  // gradient pointers of material b0 at slot 0; advanced by one batch stride per tile
+  float* o_a = p.d_albedo.ptr ? p.d_albedo.ptr + ((int64_t)b0 * p.d_albedo.sb + (int64_t)w.row * p.d_albedo.sh + w.col) : nullptr;
+  float* o_n = (has_normal && p.d_normal.ptr) ? p.d_normal.ptr + ((int64_t)b0 * p.d_normal.sb + (int64_t)w.row * p.d_normal.sh + w.col) : nullptr;
+  float* o_r = p.d_roughness.ptr ? p.d_roughness.ptr + ((int64_t)b0 * p.d_roughness.sb + (int64_t)w.row * p.d_roughness.sh + w.col) : nullptr;
+  float* o_m = p.d_metspec.ptr ? p.d_metspec.ptr + ((int64_t)b0 * p.d_metspec.sb + (int64_t)w.row * p.d_metspec.sh + w.col) : nullptr;
+  V loss_pair = splat<V>(0.0f);
+  float gi_local[3] = {0.0f, 0.0f, 0.0f};
 
   for (int k = 0; k < ntiles; ++k) {
     const int s = k % kStages;
-    const float* st = stream_smem + s * stage_floats + tid * 4;
+    const float* st = stream_smem + s * stage_floats + w.toff;
     mbar_wait(&sh.full[s], (k / kStages) & 1);
-    float araw[3][4], nraw[3][4], rough[4], mraw[3][4], gs[3][4];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) lds4(st + (SL::albedo + c) * kTileFloats, araw[c]);
-    lds4(st + SL::rough * kTileFloats, rough);
+    for (int j = 0; j < kSSlots; ++j) {
+      const float* sj = st + j * w.slot_stride;
+      V a[3][1], n[3][1], r[1], m[3][1], gs[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      if (c < SL::mc) lds4(st + (SL::met + c) * kTileFloats, mraw[c]);
-      else mraw[c][0] = mraw[c][1] = mraw[c][2] = mraw[c][3] = 0.0f;
-    }
+      for (int c = 0; c < 3; ++c) a[c][0] = lds_v(sj + (SL::albedo + c) * kTileFloats);
+      r[0] = lds_v(sj + SL::rough * kTileFloats);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) lds4(st + (SL::gsrc + c) * kTileFloats, gs[c]);
-    if (has_normal) {
+      for (int c = 0; c < 3; ++c) m[c][0] = c < SL::mc ? lds_v(sj + (SL::met + c) * kTileFloats) : splat<V>(0.0f);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) lds4(st + (SL::normal + c) * kTileFloats, nraw[c]);
-    } else {
+      for (int c = 0; c < 3; ++c) gs[c] = lds_v(sj + (SL::gsrc + c) * kTileFloats);   // grad_out, or the target image in loss mode
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { nraw[0][i] = 0.0f; nraw[1][i] = 0.0f; nraw[2][i] = 1.0f; }
-    }
-    // this warp holds its texels in registers: tell the producer (no CTA-wide barrier - warps drift freely)
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&sh.empty[s]);
-    if (w.active) {
-
-    const int b = b0 + k;
-    float d_albedo[3][4], d_normal[3][4], d_rough[4], d_met[3][4];
+      for (int c = 0; c < 3; ++c) n[c][0] = has_normal ? lds_v(sj + (SL::normal + c) * kTileFloats) : splat<V>(c == 2 ? 1.0f : 0.0f);
+      if (j == kSSlots - 1) {
+        // last read of the stage by this warp: tell the producer (no CTA-wide barrier - warps drift freely)
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&sh.empty[s]);
+      }
+      if (slot_active(w, j, p.W)) {
+        const V xs[1] = {x[j]};
+        const LightGeomT<V> hgs[1] = {hg[j]};
+        auto gout = [&](int, const V(&outv)[3][1], V(&g)[3][1]) {
 #pragma unroll
-    for (int g0 = 0; g0 < 4; g0 += G) {
-      float a[3][G], n[3][G], r[G], m[3][G], xs[G];
-      LightGeom hgs[G];
-      slice3<G>(araw, g0, a); slice3<G>(nraw, g0, n); slice3<G>(mraw, g0, m);
-#pragma unroll
-      for (int i = 0; i < G; ++i) { r[i] = rough[g0 + i]; xs[i] = x[g0 + i]; hgs[i] = hg[g0 + i]; }
-      auto gout = [&](int, const float(&outv)[3][G], float(&g)[3][G]) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-          for (int i = 0; i < G; ++i) {
+          for (int c = 0; c < 3; ++c) {
             if (kLoss) {
-              float diff = outv[c][i] - gs[c][g0 + i];
-              loss_local += diff * diff;
-              g[c][i] = 2.0f * p.loss_scale * diff;
+              const V diff = outv[c][0] - gs[c];
+              loss_pair = loss_pair + diff * diff;
+              g[c][0] = (2.0f * p.loss_scale) * diff;
             } else {
-              g[c][i] = gs[c][g0 + i];
+              g[c][0] = gs[c];
             }
           }
-      };
-      auto int_sink = [&](int, const float(&gi)[3]) {
-        if (kIntGrad) {
+        };
+        auto int_sink = [&](int, const float(&gi)[3]) {
+          if (kIntGrad) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) gi_local[c] += gi[c];
+            for (int c = 0; c < 3; ++c) gi_local[c] += gi[c];
+          }
+        };
+        V da[3][1], dn[3][1], dr[1], dm[3][1];
+#if defined(PBR_DBG_NOMATH)   // memory pipeline only (tools/build_variants.py "nomath"): results are meaningless
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { da[c][0] = a[c][0] + gs[c]; dn[c][0] = n[c][0] + hgs[0].lx; dm[c][0] = m[c][0] + xs[0]; }
+        dr[0] = r[0];
+        (void)gout; (void)int_sink;
+#else
+        ct_backward_group<WF, kLight, V, 1>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm);
+#endif
+        const int jo = j * w.slot_stride;
+        if (o_a) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) stg_v(o_a + c * p.d_albedo.sc + jo, da[c][0]);
         }
-      };
-      float da[3][G], dn[3][G], dr[G], dm[3][G];
-      ct_backward_group<WF, kLight, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm);
+        if (o_n) {
 #pragma unroll
-      for (int i = 0; i < G; ++i) {
+          for (int c = 0; c < 3; ++c) stg_v(o_n + c * p.d_normal.sc + jo, dn[c][0]);
+        }
+        if (o_r) stg_v(o_r + jo, dr[0]);
+        if (o_m) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { d_albedo[c][g0 + i] = da[c][i]; d_normal[c][g0 + i] = dn[c][i]; d_met[c][g0 + i] = dm[c][i]; }
-        d_rough[g0 + i] = dr[i];
+          for (int c = 0; c < SL::mc; ++c) stg_v(o_m + c * p.d_metspec.sc + jo, dm[c][0]);
+        }
       }
     }
-    if (p.d_albedo.ptr) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) stg4(plane_at(p.d_albedo, b, c, off_a), d_albedo[c]);
-    }
-    if (has_normal && p.d_normal.ptr) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) stg4(plane_at(p.d_normal, b, c, off_n), d_normal[c]);
-    }
-    if (p.d_roughness.ptr) stg4(plane_at(p.d_roughness, b, 0, off_r), d_rough);
-    if (p.d_metspec.ptr) {
-#pragma unroll
-      for (int c = 0; c < SL::mc; ++c) stg4(plane_at(p.d_metspec, b, c, off_m), d_met[c]);
-    }
-    }
+    if (o_a) o_a += p.d_albedo.sb;
+    if (o_n) o_n += p.d_normal.sb;
+    if (o_r) o_r += p.d_roughness.sb;
+    if (o_m) o_m += p.d_metspec.sb;
     // producer: by the time warp 0 has shaded tile k every warp has long since read stage s
     if (tid < 32 && k + kStages < ntiles) {
       mbar_wait(&sh.empty[s], (k / kStages) & 1);
@@ -379,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, PBR_STREAM_BWD_MIN_CTAS) ct_backward
 
   // CTA-level reductions: warp shuffle -> shared -> ONE atomic per CTA and value
   if (kLoss || kIntGrad) {
-    float v[4] = {kLoss ? loss_local : 0.0f, gi_local[0], gi_local[1], gi_local[2]};
+    float v[4] = {kLoss ? lane_sum(loss_pair) : 0.0f, gi_local[0], gi_local[1], gi_local[2]};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if ((j == 0 && !kLoss) || (j > 0 && !kIntGrad)) continue;
@@ -390,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, PBR_STREAM_BWD_MIN_CTAS) ct_backward
     if (tid < 4 && ((tid == 0 && kLoss) || (tid > 0 && kIntGrad))) {
       float sum = 0.0f;
 #pragma unroll
-      for (int i = 0; i < kThreads / 32; ++i) sum += s_red[i][tid];
+      for (int i = 0; i < kStreamThreads / 32; ++i) sum += s_red[i][tid];
       if (tid == 0) atomicAdd(p.loss_sum, sum);
       else atomicAdd(&p.d_intensity[tid - 1], sum);
     }

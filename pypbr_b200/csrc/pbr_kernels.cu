@@ -23,10 +23,10 @@ namespace pbr {
 #define PBR_THREADS 256
 #endif
 #ifndef PBR_FWD_MIN_CTAS
-#define PBR_FWD_MIN_CTAS 3   // __launch_bounds__ minBlocksPerSM hints (register caps), tuned on the GPU (profiles/)
+#define PBR_FWD_MIN_CTAS 4   // __launch_bounds__ minBlocksPerSM hints (register caps), tuned on the GPU (profiles/)
 #endif
 #ifndef PBR_BWD_MIN_CTAS
-#define PBR_BWD_MIN_CTAS 2
+#define PBR_BWD_MIN_CTAS 3
 #endif
 #ifndef PBR_HOIST_MATS
 #define PBR_HOIST_MATS 16    // materials a thread walks over when the light geometry is hoisted
@@ -35,7 +35,11 @@ namespace pbr {
 #define PBR_TEXELS 4         // texels per thread: 4 (float4 per plane), 2 (float2) or 1 (scalar, coalesced per warp)
 #endif
 constexpr int kTexels = PBR_TEXELS;     // texels per thread
-constexpr int kThreads = PBR_THREADS;   // threads per CTA
+constexpr int kThreads = PBR_THREADS;   // threads per CTA of the streaming kernels (conversions, blend, colour, normals)
+#ifndef PBR_CT_THREADS
+#define PBR_CT_THREADS 128   // threads per CTA of the generic Cook-Torrance kernels (168 registers x 3 CTAs per SM in the backward)
+#endif
+constexpr int kCtThreads = PBR_CT_THREADS;
 
 static std::atomic<uint64_t> g_launches{0};
 
@@ -96,11 +100,21 @@ __device__ __forceinline__ Where locate(int H, int W, bool vec_ok) {
 // ------------------------------------------------------------------------------------------------
 // Cook-Torrance kernels
 // ------------------------------------------------------------------------------------------------
+// A thread's kTexels texels are shaded as kSlots = kTexels/2 packed pairs (V = f2: FFMA2/FMUL2/FADD2).
+// -DPBR_SCALAR_LANES builds the one-texel-per-lane flavour (V = float) for A/B accuracy and speed checks.
+#if defined(PBR_SCALAR_LANES)
+typedef float V;
+#else
+typedef f2 V;
+#endif
+constexpr int kLanes = Lanes<V>::n;
+static_assert(kTexels % kLanes == 0, "texels per thread must be a multiple of the lane count");
+constexpr int kSlots = kTexels / kLanes;
 #ifndef PBR_FWD_GROUP
-#define PBR_FWD_GROUP (PBR_TEXELS > 2 ? 2 : PBR_TEXELS)   // texels shaded together (ILP) by the forward kernel
+#define PBR_FWD_GROUP 1   // pairs shaded together (ILP) by the generic forward kernel
 #endif
 #ifndef PBR_BWD_GROUP
-#define PBR_BWD_GROUP 1   // ... by the backward kernel (register pressure)
+#define PBR_BWD_GROUP 1   // ... by the generic backward kernel (register pressure)
 #endif
 
 struct CtKParams {
@@ -173,40 +187,56 @@ __device__ __forceinline__ void load_material(const CtKParams& p, const Where& w
   }
 }
 
-template <int kLight>
-__device__ __forceinline__ void grid_coords(const CtStage& S, const Where& w, float (&x)[kTexels], float& y,
-                                            LightGeom (&hg)[kTexels]) {
+// texels [kLanes*s0, kLanes*(s0+G)) of a thread's row segment as G lane-values
+template <int G, int N>
+__device__ __forceinline__ void pairs_of(const float (&src)[N], int s0, V (&dst)[G]) {
 #pragma unroll
-  for (int i = 0; i < kTexels; ++i) {
-    int col = w.col0 + i;
-    x[i] = linspace_at(S.lsx, col < S.lsx.n ? col : S.lsx.n - 1);
-  }
+  for (int i = 0; i < G; ++i)
+#pragma unroll
+    for (int k = 0; k < kLanes; ++k) lane_set(dst[i], k, src[kLanes * (s0 + i) + k]);
+}
+template <int G, int N>
+__device__ __forceinline__ void pairs_of3(const float (&src)[3][N], int s0, V (&dst)[3][G]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) pairs_of<G, N>(src[c], s0, dst[c]);
+}
+template <int G, int N>
+__device__ __forceinline__ void unpair_to(const V (&src)[G], int s0, float (&dst)[N]) {
+#pragma unroll
+  for (int i = 0; i < G; ++i)
+#pragma unroll
+    for (int k = 0; k < kLanes; ++k) dst[kLanes * (s0 + i) + k] = lane_get(src[i], k);
+}
+
+template <int kLight>
+__device__ __forceinline__ void grid_coords(const CtStage& S, const Where& w, V (&x)[kSlots], float& y,
+                                            LightGeomT<V> (&hg)[kSlots]) {
+#pragma unroll
+  for (int i = 0; i < kSlots; ++i)
+#pragma unroll
+    for (int k = 0; k < kLanes; ++k) {
+      const int col = w.col0 + kLanes * i + k;
+      lane_set(x[i], k, linspace_at(S.lsx, col < S.lsx.n ? col : S.lsx.n - 1));
+    }
   y = linspace_at(S.lsy, w.row);
   if (kLight == kLightPointHoisted) {
 #pragma unroll
-    for (int i = 0; i < kTexels; ++i)
+    for (int i = 0; i < kSlots; ++i)
       point_light_geom(S.light[0].p[0], S.light[0].p[1], S.light[0].p[2], x[i], y, S.vx, S.vy, S.vz, hg[i]);
   }
 }
 
-template <int G, int N>
-__device__ __forceinline__ void slice3(const float (&src)[3][N], int s, float (&dst)[3][G]) {
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
-#pragma unroll
-    for (int i = 0; i < G; ++i) dst[c][i] = src[c][s + i];
-}
-
 template <int WF, int kLight>
-__global__ void __launch_bounds__(kThreads, PBR_FWD_MIN_CTAS) ct_forward_kernel(const __grid_constant__ CtKParams p) {
+__global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kernel(const __grid_constant__ CtKParams p) {
   constexpr int G = PBR_FWD_GROUP;
   __shared__ CtStage S;
   stage_params(p, S);
   const Where w = locate(p.H, p.W, p.vec_ok != 0);
   if (!w.active) return;
 
-  float x[kTexels], y;
-  LightGeom hg[kTexels];
+  V x[kSlots];
+  float y;
+  LightGeomT<V> hg[kSlots];
   grid_coords<kLight>(S, w, x, y, hg);
 
   const int b0 = blockIdx.z * p.mats_per_cta;
@@ -216,29 +246,29 @@ __global__ void __launch_bounds__(kThreads, PBR_FWD_MIN_CTAS) ct_forward_kernel(
     load_material<WF>(p, w, b, araw, nraw, rough, mraw);
     float outv[3][kTexels];
 #pragma unroll
-    for (int s = 0; s < kTexels; s += G) {
-      float a[3][G], n[3][G], r[G], m[3][G], xs[G];
-      LightGeom hgs[G];
-      slice3<G>(araw, s, a); slice3<G>(nraw, s, n); slice3<G>(mraw, s, m);
+    for (int s = 0; s < kSlots; s += G) {
+      V a[3][G], n[3][G], r[G], m[3][G], xs[G];
+      LightGeomT<V> hgs[G];
+      pairs_of3<G>(araw, s, a); pairs_of3<G>(nraw, s, n); pairs_of3<G>(mraw, s, m); pairs_of<G>(rough, s, r);
 #pragma unroll
-      for (int i = 0; i < G; ++i) { r[i] = rough[s + i]; xs[i] = x[s + i]; hgs[i] = hg[s + i]; }
-      auto emit = [&](int l, const float(&v)[3][G]) {
+      for (int i = 0; i < G; ++i) { xs[i] = x[s + i]; hgs[i] = hg[s + i]; }
+      auto emit = [&](int l, const V(&v)[3][G]) {
         if (p.flags.per_light) {
           // one image per light: store this sub-group directly (64/128-bit when the group allows)
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            int vs = w.valid - s;
-            store_seg<G>(p.out.ptr + plane_off(p.out, b, c, w.row, w.col0 + s) + (int64_t)l * p.out_sl, w.vec,
-                         vs < 0 ? 0 : vs, v[c]);
+            float tv[kLanes * G];
+            unpair_to<G>(v[c], 0, tv);
+            int vs = w.valid - kLanes * s;
+            store_seg<kLanes * G>(p.out.ptr + plane_off(p.out, b, c, w.row, w.col0 + kLanes * s) + (int64_t)l * p.out_sl,
+                                  w.vec, vs < 0 ? 0 : vs, tv);
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int i = 0; i < G; ++i) outv[c][s + i] = v[c][i];
+          for (int c = 0; c < 3; ++c) unpair_to<G>(v[c], s, outv[c]);
         }
       };
-      ct_forward_group<WF, kLight, G>(S, p.flags, a, n, r, m, xs, y, hgs, emit);
+      ct_forward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, emit);
     }
     if (!p.flags.per_light) {
 #pragma unroll
@@ -259,24 +289,25 @@ __device__ __forceinline__ float warp_sum(float v) {
 //                   error is reduced warp-shuffle -> shared -> ONE atomic per CTA.
 //   p.d_intensity : per-light intensity gradients, reduced the same way.
 template <int WF, int kLight>
-__global__ void __launch_bounds__(kThreads, PBR_BWD_MIN_CTAS) ct_backward_kernel(const __grid_constant__ CtKParams p) {
+__global__ void __launch_bounds__(kCtThreads, PBR_BWD_MIN_CTAS) ct_backward_kernel(const __grid_constant__ CtKParams p) {
   constexpr int G = PBR_BWD_GROUP;
   __shared__ CtStage S;
   __shared__ float s_int[PBR_MAX_LIGHTS * 3];
-  __shared__ float s_loss[kThreads / 32];
+  __shared__ float s_loss[kCtThreads / 32];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const bool int_grad = p.d_intensity != nullptr;
   const bool is_loss = p.is_loss != 0;
   if (int_grad) {
-    for (int i = tid; i < p.flags.L * 3; i += kThreads) s_int[i] = 0.0f;
+    for (int i = tid; i < p.flags.L * 3; i += kCtThreads) s_int[i] = 0.0f;
   }
   stage_params(p, S);  // ends with __syncthreads()
   const Where w = locate(p.H, p.W, p.vec_ok != 0);
   const float live = w.active ? 1.0f : 0.0f;
   if (!w.active && !int_grad && !is_loss) return;  // nothing to reduce: edge threads may leave
 
-  float x[kTexels], y;
-  LightGeom hg[kTexels];
+  V x[kSlots];
+  float y;
+  LightGeomT<V> hg[kSlots];
   grid_coords<kLight>(S, w, x, y, hg);
 
   float loss_local = 0.0f;
@@ -287,28 +318,30 @@ __global__ void __launch_bounds__(kThreads, PBR_BWD_MIN_CTAS) ct_backward_kernel
     load_material<WF>(p, w, b, araw, nraw, rough, mraw);
     float d_albedo[3][kTexels], d_normal[3][kTexels], d_rough[kTexels], d_met[3][kTexels];
 #pragma unroll
-    for (int s = 0; s < kTexels; s += G) {
-      float a[3][G], n[3][G], r[G], m[3][G], xs[G];
-      LightGeom hgs[G];
-      slice3<G>(araw, s, a); slice3<G>(nraw, s, n); slice3<G>(mraw, s, m);
+    for (int s = 0; s < kSlots; s += G) {
+      V a[3][G], n[3][G], r[G], m[3][G], xs[G];
+      LightGeomT<V> hgs[G];
+      pairs_of3<G>(araw, s, a); pairs_of3<G>(nraw, s, n); pairs_of3<G>(mraw, s, m); pairs_of<G>(rough, s, r);
 #pragma unroll
-      for (int i = 0; i < G; ++i) { r[i] = rough[s + i]; xs[i] = x[s + i]; hgs[i] = hg[s + i]; }
-      const int vs = (w.valid - s) < 0 ? 0 : (w.valid - s);
-      auto gout = [&](int l, const float(&outv)[3][G], float(&g)[3][G]) {
+      for (int i = 0; i < G; ++i) { xs[i] = x[s + i]; hgs[i] = hg[s + i]; }
+      const int vs = (w.valid - kLanes * s) < 0 ? 0 : (w.valid - kLanes * s);   // live texels of this sub-group
+      auto gout = [&](int l, const V(&outv)[3][G], V(&g)[3][G]) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          float tv[G];
-          load_seg<G>(p.gsrc.ptr + plane_off(p.gsrc, b, c, w.row, w.col0 + s) + (int64_t)l * p.gsrc_sl, w.vec, vs, tv);
+          float tv[kLanes * G], ov[kLanes * G], gv[kLanes * G];
+          load_seg<kLanes * G>(p.gsrc.ptr + plane_off(p.gsrc, b, c, w.row, w.col0 + kLanes * s) + (int64_t)l * p.gsrc_sl, w.vec, vs, tv);
+          unpair_to<G>(outv[c], 0, ov);
 #pragma unroll
-          for (int i = 0; i < G; ++i) {
+          for (int i = 0; i < kLanes * G; ++i) {
             if (is_loss) {
-              float diff = (i < vs) ? outv[c][i] - tv[i] : 0.0f;
+              float diff = (i < vs) ? ov[i] - tv[i] : 0.0f;
               loss_local += diff * diff;
-              g[c][i] = 2.0f * p.loss_scale * diff;
+              gv[i] = 2.0f * p.loss_scale * diff;
             } else {
-              g[c][i] = (i < vs) ? tv[i] : 0.0f;
+              gv[i] = (i < vs) ? tv[i] : 0.0f;
             }
           }
+          pairs_of<G>(gv, 0, g[c]);
         }
       };
       auto int_sink = [&](int l, const float(&gi)[3]) {
@@ -320,14 +353,11 @@ __global__ void __launch_bounds__(kThreads, PBR_BWD_MIN_CTAS) ct_backward_kernel
           }
         }
       };
-      float da[3][G], dn[3][G], dr[G], dm[3][G];
-      ct_backward_group<WF, kLight, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm);
+      V da[3][G], dn[3][G], dr[G], dm[3][G];
+      ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm);
 #pragma unroll
-      for (int i = 0; i < G; ++i) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { d_albedo[c][s + i] = da[c][i]; d_normal[c][s + i] = dn[c][i]; d_met[c][s + i] = dm[c][i]; }
-        d_rough[s + i] = dr[i];
-      }
+      for (int c = 0; c < 3; ++c) { unpair_to<G>(da[c], s, d_albedo[c]); unpair_to<G>(dn[c], s, d_normal[c]); unpair_to<G>(dm[c], s, d_met[c]); }
+      unpair_to<G>(dr, s, d_rough);
     }
     if (w.active) {
       if (p.d_albedo.ptr) {
@@ -359,7 +389,7 @@ __global__ void __launch_bounds__(kThreads, PBR_BWD_MIN_CTAS) ct_backward_kernel
     atomicAdd(p.loss_sum, sum);
   }
   if (int_grad) {
-    for (int i = tid; i < p.flags.L * 3; i += kThreads) atomicAdd(&p.d_intensity[i], s_int[i]);
+    for (int i = tid; i < p.flags.L * 3; i += kCtThreads) atomicAdd(&p.d_intensity[i], s_int[i]);
   }
 }
 
@@ -506,7 +536,7 @@ __global__ void __launch_bounds__(kThreads) color_kernel(const __grid_constant__
     float v[kTexels];
     load_seg<kTexels>(p.in.ptr + plane_off(p.in, w.b, c, w.row, w.col0), w.vec, w.valid, v);
 #pragma unroll
-    for (int i = 0; i < kTexels; ++i) v[i] = p.to_linear ? srgb_decode<false>(v[i], nullptr) : srgb_encode<false>(v[i], nullptr);
+    for (int i = 0; i < kTexels; ++i) v[i] = p.to_linear ? srgb_decode<false, float>(v[i], nullptr) : srgb_encode<false, float>(v[i], nullptr);
     store_seg<kTexels>(p.out.ptr + plane_off(p.out, w.b, c, w.row, w.col0), w.vec, w.valid, v);
   }
 }
@@ -564,18 +594,18 @@ static bool plane_vec_ok(const PbrPlane& pl) {
          (pl.sh % kTexels == 0);
 }
 
-// A CTA covers a strip of up to 256 texels of blockDim.y consecutive rows.
-constexpr int kMaxBx = 256 / kTexels < kThreads ? 256 / kTexels : kThreads;
-constexpr int kMinBy = kThreads / kMaxBx;
-
-static void launch_shape(int B, int H, int W, dim3& grid, dim3& block) {
+// A CTA of `threads` threads covers a strip of up to 256 texels of blockDim.y consecutive rows.
+static void launch_shape(int B, int H, int W, dim3& grid, dim3& block, int threads = kThreads) {
+  const int max_bx = 256 / kTexels < threads ? 256 / kTexels : threads;
   int groups = (W + kTexels - 1) / kTexels;
   int bx = 1;
-  while (bx < groups && bx < kMaxBx) bx <<= 1;
-  int by = kThreads / bx;
+  while (bx < groups && bx < max_bx) bx <<= 1;
+  int by = threads / bx;
   block = dim3(bx, by, 1);
   grid = dim3((groups + bx - 1) / bx, (H + by - 1) / by, B);
 }
+// smallest blockDim.y any kernel is launched with
+constexpr int kMinBy = ((kCtThreads < kThreads ? kCtThreads : kThreads) * kTexels) / 256 > 0 ? ((kCtThreads < kThreads ? kCtThreads : kThreads) * kTexels) / 256 : 1;
 
 static int check_dims(int B, int H, int W) {
   if (B < 1 || H < 1 || W < 1 || B > 65535 || H > 65535 * kMinBy) return PBR_E_SHAPE;  // grid.z = ceil(B / mats), grid.y = ceil(H / blockDim.y), blockDim.y >= kMinBy
@@ -631,7 +661,7 @@ static int light_mode(const CtKParams& k) {
 }
 
 static void ct_launch_shape(CtKParams& k, dim3& grid, dim3& block) {
-  launch_shape(k.B, k.H, k.W, grid, block);
+  launch_shape(k.B, k.H, k.W, grid, block, kCtThreads);
   k.mats_per_cta = (light_mode(k) == kLightPointHoisted) ? (k.B < kHoistMats ? k.B : kHoistMats) : 1;
   grid.z = (k.B + k.mats_per_cta - 1) / k.mats_per_cta;
 }
@@ -684,9 +714,9 @@ static bool fits_i32(const PbrPlane& pl, int H, int W) {
 static bool stream_shape(const CtKParams& k, dim3& grid, dim3& block, int& mats) {
   if (stream_disabled() || k.force_generic || k.flags.L != 1 || !k.vec_ok || (k.W % 4) != 0 || kTexels != 4) return false;
   static const int min_bx = [] { const char* e = getenv("PBR_STREAM_MIN_BX"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
-  int groups = k.W / 4, bx = min_bx;
-  while (bx < groups && bx < kThreads) bx <<= 1;
-  int by = kThreads / bx;
+  int groups = k.W / kST, bx = min_bx < 4 / kST ? 4 / kST : min_bx;   // a row segment is a multiple of 16 bytes
+  while (bx < groups && bx < kStreamThreads) bx <<= 1;
+  int by = kStreamThreads / bx;
   int64_t gy = ((int64_t)k.H + by - 1) / by;
   if (gy > 65535) return false;
   mats = k.B < kHoistMats ? k.B : kHoistMats;

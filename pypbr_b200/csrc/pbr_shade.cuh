@@ -1,7 +1,7 @@
 // pbr_shade.cuh — staging of the view / light parameters and the per-thread drivers that shade a
-// group of N texels (N consecutive columns of one row) over L lights, forward and backward.
-// Used by the CUDA kernels (N = texels per thread, CtStage in shared memory) and by the host
-// build of the CPU test-suite (N = 1).
+// group of N lane-values V (consecutive columns of one row) over L lights, forward and backward.
+// V = f2 (two adjacent texels, packed FP32 math) in the CUDA kernels, V = float or f2 in the host
+// build of the CPU test-suite.  CtStage lives in shared memory on the device.
 #pragma once
 
 #include "pbr_math.cuh"
@@ -73,56 +73,58 @@ enum LightMode {
                           // depend on the material)
 };
 
-template <int kLight, int N>
-PBR_HD void light_geom(const CtStage& S, int l, const float (&x)[N], float y, const LightGeom (&hoisted)[N], int i,
-                       LightGeom& g) {
+template <int kLight, class V, int N>
+PBR_HD void light_geom(const CtStage& S, int l, const V (&x)[N], float y, const LightGeomT<V> (&hoisted)[N], int i,
+                       LightGeomT<V>& g) {
   if (kLight == kLightPoint) {
     point_light_geom(S.light[l].p[0], S.light[l].p[1], S.light[l].p[2], x[i], y, S.vx, S.vy, S.vz, g);
   } else if (kLight == kLightPointHoisted) {
     g = hoisted[i];
   } else {
-    g = S.light[l].geom;
+    g = splat_geom<V>(S.light[l].geom);
   }
 }
 
-PBR_HD float encode_out(float c, bool return_srgb) { return return_srgb ? srgb_encode<false>(c, nullptr) : c; }
-PBR_HD float encode_out_d(float c, bool return_srgb, float* d) {
+template <class V>
+PBR_HD V encode_out(V c, bool return_srgb) { return return_srgb ? srgb_encode<false>(c, (V*)nullptr) : c; }
+template <class V>
+PBR_HD V encode_out_d(V c, bool return_srgb, V* d) {
   if (return_srgb) return srgb_encode<true>(c, d);
-  *d = 1.0f;
+  *d = splat<V>(1.0f);
   return c;
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward: N texels of one row.  emit(l, out[3][N]) receives the encoded colour of light l
+// forward: N lane-values of one row.  emit(l, out[3][N]) receives the encoded colour of light l
 // (per-light mode) or, once, of the accumulated image (l = 0).
 // ------------------------------------------------------------------------------------------------
-template <int kWorkflow, int kLight, int N, class Emit>
-PBR_HD void ct_forward_group(const CtStage& S, const CtFlags& F, const float (&araw)[3][N], const float (&nraw)[3][N],
-                             const float (&rough)[N], const float (&mraw)[3][N], const float (&x)[N], float y,
-                             const LightGeom (&hoisted)[N], Emit emit) {
-  Texel<kWorkflow> t[N];
+template <int kWorkflow, int kLight, class V, int N, class Emit>
+PBR_HD void ct_forward_group(const CtStage& S, const CtFlags& F, const V (&araw)[3][N], const V (&nraw)[3][N],
+                             const V (&rough)[N], const V (&mraw)[3][N], const V (&x)[N], float y,
+                             const LightGeomT<V> (&hoisted)[N], Emit emit) {
+  Texel<kWorkflow, V> t[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const float a3[3] = {araw[0][i], araw[1][i], araw[2][i]};
-    const float n3[3] = {nraw[0][i], nraw[1][i], nraw[2][i]};
-    const float m3[3] = {mraw[0][i], mraw[1][i], mraw[2][i]};
+    const V a3[3] = {araw[0][i], araw[1][i], araw[2][i]};
+    const V n3[3] = {nraw[0][i], nraw[1][i], nraw[2][i]};
+    const V m3[3] = {mraw[0][i], mraw[1][i], mraw[2][i]};
     texel_setup<kWorkflow, false>(a3, n3, rough[i], m3, F.albedo_is_srgb, F.specular_is_srgb, S.vx, S.vy, S.vz, t[i]);
   }
-  float acc[3][N];
+  V acc[3][N];
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
-    for (int i = 0; i < N; ++i) acc[c][i] = 0.0f;
+    for (int i = 0; i < N; ++i) acc[c][i] = splat<V>(0.0f);
 
   const int L = (kLight == kLightPointHoisted) ? 1 : F.L;
   for (int l = 0; l < L; ++l) {
-    float outv[3][N];
+    V outv[3][N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      LightGeom g;
-      light_geom<kLight, N>(S, l, x, y, hoisted, i, g);
-      LightFwd f;
-      float col[3];
+      LightGeomT<V> g;
+      light_geom<kLight, V, N>(S, l, x, y, hoisted, i, g);
+      LightFwd<V> f;
+      V col[3];
       shade_light_fwd<kWorkflow>(t[i], g, S.light[l].inten, f, col);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -142,59 +144,59 @@ PBR_HD void ct_forward_group(const CtStage& S, const CtFlags& F, const float (&a
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: N texels of one row.
+// backward: N lane-values of one row.
 //   gout(l, out[3][N], g[3][N]) : given the encoded output of light l (or of the accumulated image,
 //        l = 0) fills g = dLoss/d out.  The plain backward ignores `out` and loads grad_out; the fused
 //        loss kernel computes 2*scale*(out - target) and accumulates the loss.
-//   int_sink(l, g_int[3])       : per-light intensity gradient summed over the N texels.
+//   int_sink(l, g_int[3])       : per-light intensity gradient summed over the texels of the group.
 // Results: d_albedo/d_normal/d_met [3][N], d_rough[N].
 // ------------------------------------------------------------------------------------------------
-template <int kWorkflow, int kLight, int N, class Gout, class IntSink>
-PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const float (&araw)[3][N],
-                              const float (&nraw)[3][N], const float (&rough)[N], const float (&mraw)[3][N],
-                              const float (&x)[N], float y, const LightGeom (&hoisted)[N], Gout gout,
-                              IntSink int_sink, float (&d_albedo)[3][N], float (&d_normal)[3][N],
-                              float (&d_rough)[N], float (&d_met)[3][N]) {
-  Texel<kWorkflow> t[N];
-  TexelGrad tg[N];
+template <int kWorkflow, int kLight, class V, int N, class Gout, class IntSink>
+PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw)[3][N], const V (&nraw)[3][N],
+                              const V (&rough)[N], const V (&mraw)[3][N], const V (&x)[N], float y,
+                              const LightGeomT<V> (&hoisted)[N], Gout gout, IntSink int_sink, V (&d_albedo)[3][N],
+                              V (&d_normal)[3][N], V (&d_rough)[N], V (&d_met)[3][N]) {
+  Texel<kWorkflow, V> t[N];
+  TexelGrad<V> tg[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const float a3[3] = {araw[0][i], araw[1][i], araw[2][i]};
-    const float n3[3] = {nraw[0][i], nraw[1][i], nraw[2][i]};
-    const float m3[3] = {mraw[0][i], mraw[1][i], mraw[2][i]};
+    const V a3[3] = {araw[0][i], araw[1][i], araw[2][i]};
+    const V n3[3] = {nraw[0][i], nraw[1][i], nraw[2][i]};
+    const V m3[3] = {mraw[0][i], mraw[1][i], mraw[2][i]};
     texel_setup<kWorkflow, true>(a3, n3, rough[i], m3, F.albedo_is_srgb, F.specular_is_srgb, S.vx, S.vy, S.vz, t[i]);
     texel_grad_zero(tg[i]);
   }
 
   const int L = (kLight == kLightPointHoisted) ? 1 : F.L;
   const bool two_pass = (!F.per_light) && L > 1;
-  float g_tot[3][N];  // two-pass only: gradient w.r.t. every per-light colour
+  V g_tot[3][N];  // two-pass only: gradient w.r.t. every per-light colour
   if (two_pass) {
     // pass 1: the accumulated image, to know where clamp(sum) gates and the slope of the encode
-    float acc[3][N];
+    V acc[3][N];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int i = 0; i < N; ++i) acc[c][i] = 0.0f;
+      for (int i = 0; i < N; ++i) acc[c][i] = splat<V>(0.0f);
     for (int l = 0; l < L; ++l) {
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        LightGeom g;
-        light_geom<kLight, N>(S, l, x, y, hoisted, i, g);
-        LightFwd f;
-        float col[3];
+        LightGeomT<V> g;
+        light_geom<kLight, V, N>(S, l, x, y, hoisted, i, g);
+        LightFwd<V> f;
+        V col[3];
         shade_light_fwd<kWorkflow>(t[i], g, S.light[l].inten, f, col);
 #pragma unroll
         for (int c = 0; c < 3; ++c) acc[c][i] = xadd(acc[c][i], col[c]);
       }
     }
-    float outv[3][N], slope[3][N];
+    V outv[3][N], slope[3][N];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        outv[c][i] = encode_out_d(clamp01(acc[c][i]), F.return_srgb, &slope[c][i]);
-        slope[c][i] = gated(slope[c][i], acc[c][i], clamp01(acc[c][i]));
+        const V cl = clamp01(acc[c][i]);
+        outv[c][i] = encode_out_d(cl, F.return_srgb, &slope[c][i]);
+        slope[c][i] = gated(slope[c][i], acc[c][i], cl);
       }
     gout(0, outv, g_tot);
 #pragma unroll
@@ -204,13 +206,13 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const float (&
   }
 
   for (int l = 0; l < L; ++l) {
-    LightGeom g[N];
-    LightFwd f[N];
-    float outv[3][N], slope[3][N], gl[3][N];
+    LightGeomT<V> g[N];
+    LightFwd<V> f[N];
+    V outv[3][N], slope[3][N], gl[3][N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      light_geom<kLight, N>(S, l, x, y, hoisted, i, g[i]);
-      float col[3];
+      light_geom<kLight, V, N>(S, l, x, y, hoisted, i, g[i]);
+      V col[3];
       shade_light_fwd<kWorkflow>(t[i], g[i], S.light[l].inten, f[i], col);
       if (!two_pass) {
 #pragma unroll
@@ -227,19 +229,19 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const float (&
     float gi_sum[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const float gc[3] = {two_pass ? g_tot[0][i] : gl[0][i], two_pass ? g_tot[1][i] : gl[1][i],
-                           two_pass ? g_tot[2][i] : gl[2][i]};
-      float gi[3];
+      const V gc[3] = {two_pass ? g_tot[0][i] : gl[0][i], two_pass ? g_tot[1][i] : gl[1][i],
+                       two_pass ? g_tot[2][i] : gl[2][i]};
+      V gi[3];
       shade_light_bwd<kWorkflow>(t[i], g[i], S.light[l].inten, f[i], gc, tg[i], gi);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) gi_sum[c] += gi[c];
+      for (int c = 0; c < 3; ++c) gi_sum[c] += lane_sum(gi[c]);
     }
     int_sink(l, gi_sum);
   }
 
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    float da[3], dn[3], dm[3], dr;
+    V da[3], dn[3], dm[3], dr;
     texel_finish_grad<kWorkflow>(t[i], tg[i], rough[i], S.vx, S.vy, S.vz, da, dn, &dr, dm);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {

@@ -17,81 +17,99 @@ struct Dims {
   int B, H, W, L;
 };
 
-template <int WF, bool HASN, int LIGHT>
+// One call shades Lanes<V>::n horizontally adjacent texels (V = float: 1, V = f2: 2, the packing the
+// CUDA kernels use); at a ragged right edge the second lane repeats the last column and is dropped.
+template <int WF, bool HASN, int LIGHT, class V>
 void fwd_impl(const Dims& d, const CtStage& S, const CtFlags& F, const float* albedo, const float* normal,
               const float* rough, const float* metspec, float* out) {
+  constexpr int NL = Lanes<V>::n;
   const int mc = WF == 0 ? 1 : 3;  // WF 2: metallic with 3 channels
   const int64_t HW = (int64_t)d.H * d.W;
   for (int b = 0; b < d.B; ++b)
     for (int yy = 0; yy < d.H; ++yy)
-      for (int xx = 0; xx < d.W; ++xx) {
-        const int64_t o = (int64_t)yy * d.W + xx;
-        float a[3][1], n[3][1] = {{0}, {0}, {1}}, r[1], m[3][1] = {{0}, {0}, {0}}, x[1];
-        for (int c = 0; c < 3; ++c) a[c][0] = albedo[(b * 3 + c) * HW + o];
-        if (HASN)
-          for (int c = 0; c < 3; ++c) n[c][0] = normal[(b * 3 + c) * HW + o];
-        r[0] = rough[b * HW + o];
-        for (int c = 0; c < mc; ++c) m[c][0] = metspec[(b * mc + c) * HW + o];
-        x[0] = linspace_at(S.lsx, xx);
+      for (int xx = 0; xx < d.W; xx += NL) {
+        int64_t o[2];
+        for (int k = 0; k < NL; ++k) o[k] = (int64_t)yy * d.W + (xx + k < d.W ? xx + k : d.W - 1);
+        const int live = (xx + NL <= d.W) ? NL : d.W - xx;
+        V a[3][1], n[3][1], r[1], m[3][1], x[1];
+        for (int k = 0; k < NL; ++k) {
+          for (int c = 0; c < 3; ++c) lane_set(a[c][0], k, albedo[(b * 3 + c) * HW + o[k]]);
+          for (int c = 0; c < 3; ++c) lane_set(n[c][0], k, HASN ? normal[(b * 3 + c) * HW + o[k]] : (c == 2 ? 1.0f : 0.0f));
+          lane_set(r[0], k, rough[b * HW + o[k]]);
+          for (int c = 0; c < 3; ++c) lane_set(m[c][0], k, c < mc ? metspec[(b * mc + c) * HW + o[k]] : 0.0f);
+          lane_set(x[0], k, linspace_at(S.lsx, xx + k < d.W ? xx + k : d.W - 1));
+        }
         float y = linspace_at(S.lsy, yy);
-        auto emit = [&](int l, const float(&v)[3][1]) {
-          for (int c = 0; c < 3; ++c) {
-            int64_t idx = F.per_light ? (((int64_t)b * d.L + l) * 3 + c) * HW + o : ((int64_t)b * 3 + c) * HW + o;
-            out[idx] = v[c][0];
-          }
+        auto emit = [&](int l, const V(&v)[3][1]) {
+          for (int k = 0; k < live; ++k)
+            for (int c = 0; c < 3; ++c) {
+              int64_t idx = F.per_light ? (((int64_t)b * d.L + l) * 3 + c) * HW + o[k] : ((int64_t)b * 3 + c) * HW + o[k];
+              out[idx] = lane_get(v[c][0], k);
+            }
         };
-        LightGeom hg[1];
+        LightGeomT<V> hg[1];
         if (LIGHT == kLightPointHoisted)
           point_light_geom(S.light[0].p[0], S.light[0].p[1], S.light[0].p[2], x[0], y, S.vx, S.vy, S.vz, hg[0]);
-        ct_forward_group<WF, LIGHT, 1>(S, F, a, n, r, m, x, y, hg, emit);
+        ct_forward_group<WF, LIGHT, V, 1>(S, F, a, n, r, m, x, y, hg, emit);
       }
 }
 
-template <int WF, bool HASN, int LIGHT>
+template <int WF, bool HASN, int LIGHT, class V>
 void bwd_impl(const Dims& d, const CtStage& S, const CtFlags& F, const float* albedo, const float* normal,
               const float* rough, const float* metspec, const float* grad_out, const float* target,
               float loss_scale, double* loss_sum, float* d_albedo, float* d_normal, float* d_rough, float* d_met,
               double* d_int) {
+  constexpr int NL = Lanes<V>::n;
   const int mc = WF == 0 ? 1 : 3;  // WF 2: metallic with 3 channels
   const int64_t HW = (int64_t)d.H * d.W;
   for (int b = 0; b < d.B; ++b)
     for (int yy = 0; yy < d.H; ++yy)
-      for (int xx = 0; xx < d.W; ++xx) {
-        const int64_t o = (int64_t)yy * d.W + xx;
-        float a[3][1], n[3][1] = {{0}, {0}, {1}}, r[1], m[3][1] = {{0}, {0}, {0}}, x[1];
-        for (int c = 0; c < 3; ++c) a[c][0] = albedo[(b * 3 + c) * HW + o];
-        if (HASN)
-          for (int c = 0; c < 3; ++c) n[c][0] = normal[(b * 3 + c) * HW + o];
-        r[0] = rough[b * HW + o];
-        for (int c = 0; c < mc; ++c) m[c][0] = metspec[(b * mc + c) * HW + o];
-        x[0] = linspace_at(S.lsx, xx);
+      for (int xx = 0; xx < d.W; xx += NL) {
+        int64_t o[2];
+        for (int k = 0; k < NL; ++k) o[k] = (int64_t)yy * d.W + (xx + k < d.W ? xx + k : d.W - 1);
+        const int live = (xx + NL <= d.W) ? NL : d.W - xx;
+        V a[3][1], n[3][1], r[1], m[3][1], x[1];
+        for (int k = 0; k < NL; ++k) {
+          for (int c = 0; c < 3; ++c) lane_set(a[c][0], k, albedo[(b * 3 + c) * HW + o[k]]);
+          for (int c = 0; c < 3; ++c) lane_set(n[c][0], k, HASN ? normal[(b * 3 + c) * HW + o[k]] : (c == 2 ? 1.0f : 0.0f));
+          lane_set(r[0], k, rough[b * HW + o[k]]);
+          for (int c = 0; c < 3; ++c) lane_set(m[c][0], k, c < mc ? metspec[(b * mc + c) * HW + o[k]] : 0.0f);
+          lane_set(x[0], k, linspace_at(S.lsx, xx + k < d.W ? xx + k : d.W - 1));
+        }
         float y = linspace_at(S.lsy, yy);
-        auto gout = [&](int l, const float(&outv)[3][1], float(&g)[3][1]) {
-          for (int c = 0; c < 3; ++c) {
-            int64_t idx = F.per_light ? (((int64_t)b * d.L + l) * 3 + c) * HW + o : ((int64_t)b * 3 + c) * HW + o;
-            if (target) {
-              float diff = outv[c][0] - target[idx];
-              *loss_sum += (double)diff * diff;
-              g[c][0] = 2.0f * loss_scale * diff;
-            } else {
-              g[c][0] = grad_out[idx];
+        auto gout = [&](int l, const V(&outv)[3][1], V(&g)[3][1]) {
+          for (int c = 0; c < 3; ++c)
+            for (int k = 0; k < NL; ++k) {
+              if (k >= live) {  // dropped lane: contributes nothing (the kernels zero it the same way)
+                lane_set(g[c][0], k, 0.0f);
+                continue;
+              }
+              int64_t idx = F.per_light ? (((int64_t)b * d.L + l) * 3 + c) * HW + o[k] : ((int64_t)b * 3 + c) * HW + o[k];
+              if (target) {
+                float diff = lane_get(outv[c][0], k) - target[idx];
+                *loss_sum += (double)diff * diff;
+                lane_set(g[c][0], k, 2.0f * loss_scale * diff);
+              } else {
+                lane_set(g[c][0], k, grad_out[idx]);
+              }
             }
-          }
         };
         auto sink = [&](int l, const float(&gi)[3]) {
           if (d_int)
             for (int c = 0; c < 3; ++c) d_int[3 * l + c] += gi[c];
         };
-        float da[3][1], dn[3][1], dr[1], dm[3][1];
-        LightGeom hg[1];
+        V da[3][1], dn[3][1], dr[1], dm[3][1];
+        LightGeomT<V> hg[1];
         if (LIGHT == kLightPointHoisted)
           point_light_geom(S.light[0].p[0], S.light[0].p[1], S.light[0].p[2], x[0], y, S.vx, S.vy, S.vz, hg[0]);
-        ct_backward_group<WF, LIGHT, 1>(S, F, a, n, r, m, x, y, hg, gout, sink, da, dn, dr, dm);
-        for (int c = 0; c < 3; ++c) d_albedo[(b * 3 + c) * HW + o] = da[c][0];
-        if (HASN && d_normal)
-          for (int c = 0; c < 3; ++c) d_normal[(b * 3 + c) * HW + o] = dn[c][0];
-        d_rough[b * HW + o] = dr[0];
-        for (int c = 0; c < mc; ++c) d_met[(b * mc + c) * HW + o] = dm[c][0];
+        ct_backward_group<WF, LIGHT, V, 1>(S, F, a, n, r, m, x, y, hg, gout, sink, da, dn, dr, dm);
+        for (int k = 0; k < live; ++k) {
+          for (int c = 0; c < 3; ++c) d_albedo[(b * 3 + c) * HW + o[k]] = lane_get(da[c][0], k);
+          if (HASN && d_normal)
+            for (int c = 0; c < 3; ++c) d_normal[(b * 3 + c) * HW + o[k]] = lane_get(dn[c][0], k);
+          d_rough[b * HW + o[k]] = lane_get(dr[0], k);
+          for (int c = 0; c < mc; ++c) d_met[(b * mc + c) * HW + o[k]] = lane_get(dm[c][0], k);
+        }
       }
 }
 
@@ -104,31 +122,37 @@ void make_stage(const Dims& d, int light_type, float light_size, const float* vi
   for (int l = 0; l < d.L; ++l) stage_light(l, lights, inten, light_type == 1, S.vx, S.vy, S.vz, S.light[l]);
 }
 
-// light mode: directional / point / point-hoisted (the kernels pick the hoisted variant for L == 1)
-#define DISPATCH(fn, ...)                                                                   \
+// light mode: directional / point / point-hoisted (the kernels pick the hoisted variant for L == 1).
+// `force_generic` bit 0: generic light mode; bit 1: V = f2 (two texels per call, the packing of the CUDA kernels).
+#define DISPATCH_V(fn, V, ...)                                                             \
   do {                                                                                      \
-    int lm = light_type == 1 ? ((L == 1 && !force_generic) ? 2 : 1) : 0;                    \
+    int lm = light_type == 1 ? ((L == 1 && !(force_generic & 1)) ? 2 : 1) : 0;              \
     int key = (workflow * 2 + (normal != nullptr)) * 3 + lm;                                \
     switch (key) {                                                                          \
-      case 0: fn<0, false, 0>(__VA_ARGS__); break;                                          \
-      case 1: fn<0, false, 1>(__VA_ARGS__); break;                                          \
-      case 2: fn<0, false, 2>(__VA_ARGS__); break;                                          \
-      case 3: fn<0, true, 0>(__VA_ARGS__); break;                                           \
-      case 4: fn<0, true, 1>(__VA_ARGS__); break;                                           \
-      case 5: fn<0, true, 2>(__VA_ARGS__); break;                                           \
-      case 6: fn<1, false, 0>(__VA_ARGS__); break;                                          \
-      case 7: fn<1, false, 1>(__VA_ARGS__); break;                                          \
-      case 8: fn<1, false, 2>(__VA_ARGS__); break;                                          \
-      case 9: fn<1, true, 0>(__VA_ARGS__); break;                                           \
-      case 10: fn<1, true, 1>(__VA_ARGS__); break;                                          \
-      case 11: fn<1, true, 2>(__VA_ARGS__); break;                                          \
-      case 12: fn<2, false, 0>(__VA_ARGS__); break;                                         \
-      case 13: fn<2, false, 1>(__VA_ARGS__); break;                                         \
-      case 14: fn<2, false, 2>(__VA_ARGS__); break;                                         \
-      case 15: fn<2, true, 0>(__VA_ARGS__); break;                                          \
-      case 16: fn<2, true, 1>(__VA_ARGS__); break;                                          \
-      case 17: fn<2, true, 2>(__VA_ARGS__); break;                                          \
+      case 0: fn<0, false, 0, V>(__VA_ARGS__); break;                                       \
+      case 1: fn<0, false, 1, V>(__VA_ARGS__); break;                                       \
+      case 2: fn<0, false, 2, V>(__VA_ARGS__); break;                                       \
+      case 3: fn<0, true, 0, V>(__VA_ARGS__); break;                                        \
+      case 4: fn<0, true, 1, V>(__VA_ARGS__); break;                                        \
+      case 5: fn<0, true, 2, V>(__VA_ARGS__); break;                                        \
+      case 6: fn<1, false, 0, V>(__VA_ARGS__); break;                                       \
+      case 7: fn<1, false, 1, V>(__VA_ARGS__); break;                                       \
+      case 8: fn<1, false, 2, V>(__VA_ARGS__); break;                                       \
+      case 9: fn<1, true, 0, V>(__VA_ARGS__); break;                                        \
+      case 10: fn<1, true, 1, V>(__VA_ARGS__); break;                                       \
+      case 11: fn<1, true, 2, V>(__VA_ARGS__); break;                                       \
+      case 12: fn<2, false, 0, V>(__VA_ARGS__); break;                                      \
+      case 13: fn<2, false, 1, V>(__VA_ARGS__); break;                                      \
+      case 14: fn<2, false, 2, V>(__VA_ARGS__); break;                                      \
+      case 15: fn<2, true, 0, V>(__VA_ARGS__); break;                                       \
+      case 16: fn<2, true, 1, V>(__VA_ARGS__); break;                                       \
+      case 17: fn<2, true, 2, V>(__VA_ARGS__); break;                                       \
     }                                                                                       \
+  } while (0)
+#define DISPATCH(fn, ...)                                                                   \
+  do {                                                                                      \
+    if (force_generic & 2) DISPATCH_V(fn, f2, __VA_ARGS__);                                 \
+    else DISPATCH_V(fn, float, __VA_ARGS__);                                                \
   } while (0)
 
 }  // namespace
@@ -210,7 +234,7 @@ void hs_linspace(float start, float end, int n, float* out) {
 
 void hs_srgb(int64_t n, int to_linear, const float* in, float* out) {
   for (int64_t i = 0; i < n; ++i)
-    out[i] = to_linear ? srgb_decode<false>(in[i], nullptr) : srgb_encode<false>(in[i], nullptr);
+    out[i] = to_linear ? srgb_decode<false, float>(in[i], nullptr) : srgb_encode<false, float>(in[i], nullptr);
 }
 
 void hs_ingest_normal(int64_t n_texels, int channels, const float* in, float* out) {

@@ -173,7 +173,8 @@ def test_full_size_properties():
     """
     At a BASELINE-sized image (1024x1024, B=4) the oracle is too slow, so size-independent properties:
     a batch equals its per-material calls bit-for-bit; the hoisted single-light path equals the generic
-    multi-light path with a second, zero-intensity light; a horizontal flip of the maps (with the
+    multi-light path with a second, zero-intensity light to a few ulp (same per-texel code, but the compiler
+    may contract multiply-adds of the tolerant zone differently in the two kernels); a horizontal flip of the maps (with the
     normal's x sign) under a mirrored light mirrors the image; unclamped output is linear in intensity.
     """
     from pypbr_b200.models import CookTorranceBRDF
@@ -191,7 +192,8 @@ def test_full_size_properties():
         assert torch.equal(brdf(one, view, lights, inten, 1.0), full[b])
     two = torch.stack([lights, torch.tensor([0.3, -0.2, 0.8])])
     two_i = torch.stack([inten, torch.zeros(3)])
-    assert torch.equal(brdf(mat, view, two, two_i, 1.0), full)
+    multi = brdf(mat, view, two, two_i, 1.0)
+    assert bool(((multi - full).abs() <= 2e-6 * full.abs() + 2e-6 * full.abs().mean()).all())
     # mirror symmetry
     flipped = mat.clone().flip_horizontal()
     lf = lights * torch.tensor([-1.0, 1.0, 1.0])

@@ -14,22 +14,18 @@ def v(**kw):
 
 
 VARIANTS = {
-    "strict": ["-DPBR_STRICT_IEEE"],
+    "scalar": ["-DPBR_SCALAR_LANES", "-DPBR_FWD_GROUP=2", "-DPBR_CT_THREADS=256", "-DPBR_FWD_MIN_CTAS=3", "-DPBR_BWD_MIN_CTAS=2",
+               "-DPBR_STREAM_THREADS=256", "-DPBR_STREAM_FWD_MIN_CTAS=2", "-DPBR_STREAM_BWD_MIN_CTAS=2"],   # one texel per lane (V = float): accuracy / speed reference
     "default": [],
-    # streamed kernels: stages / CTAs per SM (register cap) / texels shaded together / materials per CTA walk
-    "f2g2": v(stream_fwd_min_ctas=2),
-    "f2g4": v(stream_fwd_min_ctas=2, stream_fwd_group=4),
-    "f3g1": v(stream_fwd_group=1),
-    "f4g1": v(stream_fwd_min_ctas=4, stream_fwd_group=1),
-    "f2g2_s3": v(stream_fwd_min_ctas=2, stream_stages=3),
-    "b2g2": v(stream_bwd_group=2),
-    "b3g1": v(stream_bwd_min_ctas=3),
-    "h8": v(hoist_mats=8),
-    "h32": v(hoist_mats=32),
-    "h64": v(hoist_mats=64),
-    "t128_f6b4": v(threads=128, stream_fwd_min_ctas=6, stream_bwd_min_ctas=4),
-    "t128_f4b4_s3": v(threads=128, stream_fwd_min_ctas=4, stream_bwd_min_ctas=4, stream_stages=3),
-    "t512_f1b1": v(threads=512, stream_fwd_min_ctas=1, stream_bwd_min_ctas=1),
+    "t128x4_f4b3_s3": v(stream_stages=3),
+    "t128x4_f4b4": v(stream_bwd_min_ctas=4),
+    "t128x4_f3b3": v(stream_fwd_min_ctas=3),
+    "t256x4_f2b2": v(stream_threads=256, stream_fwd_min_ctas=2, stream_bwd_min_ctas=2),
+    "t256x2_f3b2": v(stream_threads=256, stream_texels=2, stream_fwd_min_ctas=3, stream_bwd_min_ctas=2),
+    "t128x2_f6b4": v(stream_texels=2, stream_fwd_min_ctas=6, stream_bwd_min_ctas=4),
+    "t64x4_f8b6": v(stream_threads=64, stream_fwd_min_ctas=8, stream_bwd_min_ctas=6),
+    # memory pipeline only (no shading math): the floor of the TMA-in / STG-out design
+    "nomath": ["-DPBR_DBG_NOMATH"],
 }
 
 

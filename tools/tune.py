@@ -20,10 +20,21 @@ from bench import synth_maps  # noqa: E402
 
 B, H, W, L = int(os.environ.get("TUNE_B", 32)), 1024, 1024, int(os.environ.get("TUNE_L", 1))
 dev = torch.device("cuda:0")
-maps = synth_maps(B, H, W, dev, 3)
-out = torch.empty(B, 3, H, W, device=dev)
-go = torch.rand(B, 3, H, W, device=dev)
-grads = {k: torch.empty_like(v) for k, v in maps.items()}
+PAD = int(os.environ.get("TUNE_PAD", 0))   # extra rows per plane: breaks the power-of-two plane stride
+
+
+def padded(t):
+    if PAD == 0:
+        return t
+    big = torch.empty(t.shape[0], t.shape[1], H + PAD, W, device=dev)
+    big[:, :, :H].copy_(t)
+    return big[:, :, :H]
+
+
+maps = {k: padded(v) for k, v in synth_maps(B, H, W, dev, 3).items()}
+out = padded(torch.empty(B, 3, H, W, device=dev))
+go = padded(torch.rand(B, 3, H, W, device=dev))
+grads = {k: padded(torch.empty_like(v)) for k, v in maps.items()}
 import math
 if L == 1:
     lights = [0.1, 0.1, 1.0]; inten = [1.0, 1.0, 1.0]
@@ -48,7 +59,9 @@ stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 results = {}
 ref_out = ref_g = None
 paths = sorted(glob.glob(os.path.join(ROOT, "pypbr_b200", "lib", "variants", "libpbrcuda_*.so")))
-paths.sort(key=lambda p: (not p.endswith("_strict.so"), p))  # strict first: it is the accuracy reference
+if os.environ.get("TUNE_ONLY"):
+    paths = [p for p in paths if os.path.basename(p)[len("libpbrcuda_"):-3] in os.environ["TUNE_ONLY"].split(",")]
+paths.sort(key=lambda p: (not p.endswith("_scalar.so"), p))  # scalar-lane build first: it is the accuracy reference
 texels = B * H * W
 for path in paths:
     name = os.path.basename(path)[len("libpbrcuda_"):-3]
@@ -88,7 +101,7 @@ for path in paths:
     fb, bb = texels * 44 / times["fwd"] / 1e6, texels * 76 / times["bwd"] / 1e6
     tot = texels * L / ((times["fwd"] + times["bwd"]) * 1e-3) / 1e9
     results[name] = dict(fwd_ms=times["fwd"], bwd_ms=times["bwd"], fwd_gbs=fb, bwd_gbs=bb, gtexel_lights=tot,
-                         max_abs_out_vs_strict=dout, max_rel_grad_vs_strict=dg)
+                         max_abs_out_vs_scalar=dout, max_rel_grad_vs_scalar=dg)
     print(f"{name:20s} fwd {times['fwd']:7.3f} ms {fb:7.0f} GB/s | bwd {times['bwd']:7.3f} ms {bb:7.0f} GB/s | "
           f"{tot:6.2f} Gtexel-lights/s | d_out {dout:.2e} d_grad {dg:.2e}", flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
