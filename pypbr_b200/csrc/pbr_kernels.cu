@@ -83,24 +83,31 @@ struct Where {
   int b, row, col0, valid;
   bool active, vec;
 };
-__device__ __forceinline__ Where locate(int H, int W, bool vec_ok) {
+template <int N>
+__device__ __forceinline__ Where locate_n(int H, int W, bool vec_ok) {
   Where w;
   w.b = blockIdx.z;
   int row = blockIdx.y * blockDim.y + threadIdx.y;
-  int col0 = (blockIdx.x * blockDim.x + threadIdx.x) * kTexels;
+  int col0 = (blockIdx.x * blockDim.x + threadIdx.x) * N;
   w.active = row < H && col0 < W;
   w.row = row < H ? row : H - 1;
-  w.col0 = col0 < W ? col0 : ((W - 1) / kTexels) * kTexels;
+  w.col0 = col0 < W ? col0 : ((W - 1) / N) * N;
   int rem = W - w.col0;
-  w.valid = rem < kTexels ? rem : kTexels;
-  w.vec = vec_ok && w.valid == kTexels;
+  w.valid = rem < N ? rem : N;
+  w.vec = vec_ok && w.valid == N;
   return w;
 }
+__device__ __forceinline__ Where locate(int H, int W, bool vec_ok) { return locate_n<kTexels>(H, W, vec_ok); }
 
 // ------------------------------------------------------------------------------------------------
 // Cook-Torrance kernels
 // ------------------------------------------------------------------------------------------------
-// A thread's kTexels texels are shaded as kSlots = kTexels/2 packed pairs (V = f2: FFMA2/FMUL2/FADD2).
+// A thread of the generic kernels owns kCtTexels consecutive texels of one row, shaded as kSlots = kCtTexels/2
+// packed pairs (V = f2: FFMA2/FMUL2/FADD2).  One pair per thread keeps the adjoint's working set in registers.
+#ifndef PBR_CT_TEXELS
+#define PBR_CT_TEXELS 2
+#endif
+constexpr int kCtTexels = PBR_CT_TEXELS;
 // -DPBR_SCALAR_LANES builds the one-texel-per-lane flavour (V = float) for A/B accuracy and speed checks.
 #if defined(PBR_SCALAR_LANES)
 typedef float V;
@@ -108,8 +115,8 @@ typedef float V;
 typedef f2 V;
 #endif
 constexpr int kLanes = Lanes<V>::n;
-static_assert(kTexels % kLanes == 0, "texels per thread must be a multiple of the lane count");
-constexpr int kSlots = kTexels / kLanes;
+static_assert(kCtTexels % kLanes == 0, "texels per thread must be a multiple of the lane count");
+constexpr int kSlots = kCtTexels / kLanes;
 #ifndef PBR_FWD_GROUP
 #define PBR_FWD_GROUP 1   // pairs shaded together (ILP) by the generic forward kernel
 #endif
@@ -162,27 +169,27 @@ __device__ __forceinline__ void stage_params(const CtKParams& p, CtStage& S) {
 }
 
 template <int WF>
-__device__ __forceinline__ void load_material(const CtKParams& p, const Where& w, int b, float (&araw)[3][kTexels],
-                                              float (&nraw)[3][kTexels], float (&rough)[kTexels],
-                                              float (&mraw)[3][kTexels]) {
+__device__ __forceinline__ void load_material(const CtKParams& p, const Where& w, int b, float (&araw)[3][kCtTexels],
+                                              float (&nraw)[3][kCtTexels], float (&rough)[kCtTexels],
+                                              float (&mraw)[3][kCtTexels]) {
 #pragma unroll
-  for (int c = 0; c < 3; ++c) load_seg<kTexels>(p.albedo.ptr + plane_off(p.albedo, b, c, w.row, w.col0), w.vec, w.valid, araw[c]);
+  for (int c = 0; c < 3; ++c) load_seg<kCtTexels>(p.albedo.ptr + plane_off(p.albedo, b, c, w.row, w.col0), w.vec, w.valid, araw[c]);
   if (p.normal.ptr) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) load_seg<kTexels>(p.normal.ptr + plane_off(p.normal, b, c, w.row, w.col0), w.vec, w.valid, nraw[c]);
+    for (int c = 0; c < 3; ++c) load_seg<kCtTexels>(p.normal.ptr + plane_off(p.normal, b, c, w.row, w.col0), w.vec, w.valid, nraw[c]);
   } else {
 #pragma unroll
-    for (int i = 0; i < kTexels; ++i) { nraw[0][i] = 0.0f; nraw[1][i] = 0.0f; nraw[2][i] = 1.0f; }
+    for (int i = 0; i < kCtTexels; ++i) { nraw[0][i] = 0.0f; nraw[1][i] = 0.0f; nraw[2][i] = 1.0f; }
   }
-  load_seg<kTexels>(p.roughness.ptr + plane_off(p.roughness, b, 0, w.row, w.col0), w.vec, w.valid, rough);
+  load_seg<kCtTexels>(p.roughness.ptr + plane_off(p.roughness, b, 0, w.row, w.col0), w.vec, w.valid, rough);
   constexpr int mc = WF == 0 ? 1 : 3;  // WF: 0 metallic (1 ch), 1 specular, 2 metallic (3 ch)
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     if (c < mc) {
-      load_seg<kTexels>(p.metspec.ptr + plane_off(p.metspec, b, c, w.row, w.col0), w.vec, w.valid, mraw[c]);
+      load_seg<kCtTexels>(p.metspec.ptr + plane_off(p.metspec, b, c, w.row, w.col0), w.vec, w.valid, mraw[c]);
     } else {
 #pragma unroll
-      for (int i = 0; i < kTexels; ++i) mraw[c][i] = 0.0f;
+      for (int i = 0; i < kCtTexels; ++i) mraw[c][i] = 0.0f;
     }
   }
 }
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kerne
   constexpr int G = PBR_FWD_GROUP;
   __shared__ CtStage S;
   stage_params(p, S);
-  const Where w = locate(p.H, p.W, p.vec_ok != 0);
+  const Where w = locate_n<kCtTexels>(p.H, p.W, p.vec_ok != 0);
   if (!w.active) return;
 
   V x[kSlots];
@@ -242,9 +249,9 @@ __global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kerne
   const int b0 = blockIdx.z * p.mats_per_cta;
   const int b1 = min(b0 + p.mats_per_cta, p.B);
   for (int b = b0; b < b1; ++b) {
-    float araw[3][kTexels], nraw[3][kTexels], rough[kTexels], mraw[3][kTexels];
+    float araw[3][kCtTexels], nraw[3][kCtTexels], rough[kCtTexels], mraw[3][kCtTexels];
     load_material<WF>(p, w, b, araw, nraw, rough, mraw);
-    float outv[3][kTexels];
+    float outv[3][kCtTexels];
 #pragma unroll
     for (int s = 0; s < kSlots; s += G) {
       V a[3][G], n[3][G], r[G], m[3][G], xs[G];
@@ -273,10 +280,22 @@ __global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kerne
     if (!p.flags.per_light) {
 #pragma unroll
       for (int c = 0; c < 3; ++c)
-        store_seg<kTexels>(p.out.ptr + plane_off(p.out, b, c, w.row, w.col0), w.vec, w.valid, outv[c]);
+        store_seg<kCtTexels>(p.out.ptr + plane_off(p.out, b, c, w.row, w.col0), w.vec, w.valid, outv[c]);
     }
   }
 }
+
+// per-thread asynchronous copies global -> shared (LDGSTS) for the backward kernel's grad_out / target ring
+constexpr int kRing = 4;
+__device__ __forceinline__ void cp_async8(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -294,6 +313,7 @@ __global__ void __launch_bounds__(kCtThreads, PBR_BWD_MIN_CTAS) ct_backward_kern
   __shared__ CtStage S;
   __shared__ float s_int[PBR_MAX_LIGHTS * 3];
   __shared__ float s_loss[kCtThreads / 32];
+  __shared__ __align__(16) float s_ring[kRing * 3 * kCtThreads * kLanes * PBR_BWD_GROUP];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const bool int_grad = p.d_intensity != nullptr;
   const bool is_loss = p.is_loss != 0;
@@ -301,7 +321,7 @@ __global__ void __launch_bounds__(kCtThreads, PBR_BWD_MIN_CTAS) ct_backward_kern
     for (int i = tid; i < p.flags.L * 3; i += kCtThreads) s_int[i] = 0.0f;
   }
   stage_params(p, S);  // ends with __syncthreads()
-  const Where w = locate(p.H, p.W, p.vec_ok != 0);
+  const Where w = locate_n<kCtTexels>(p.H, p.W, p.vec_ok != 0);
   const float live = w.active ? 1.0f : 0.0f;
   if (!w.active && !int_grad && !is_loss) return;  // nothing to reduce: edge threads may leave
 
@@ -314,9 +334,9 @@ __global__ void __launch_bounds__(kCtThreads, PBR_BWD_MIN_CTAS) ct_backward_kern
   const int b0 = blockIdx.z * p.mats_per_cta;
   const int b1 = min(b0 + p.mats_per_cta, p.B);
   for (int b = b0; b < b1; ++b) {
-    float araw[3][kTexels], nraw[3][kTexels], rough[kTexels], mraw[3][kTexels];
+    float araw[3][kCtTexels], nraw[3][kCtTexels], rough[kCtTexels], mraw[3][kCtTexels];
     load_material<WF>(p, w, b, araw, nraw, rough, mraw);
-    float d_albedo[3][kTexels], d_normal[3][kTexels], d_rough[kTexels], d_met[3][kTexels];
+    float d_albedo[3][kCtTexels], d_normal[3][kCtTexels], d_rough[kCtTexels], d_met[3][kCtTexels];
 #pragma unroll
     for (int s = 0; s < kSlots; s += G) {
       V a[3][G], n[3][G], r[G], m[3][G], xs[G];
@@ -325,20 +345,60 @@ __global__ void __launch_bounds__(kCtThreads, PBR_BWD_MIN_CTAS) ct_backward_kern
 #pragma unroll
       for (int i = 0; i < G; ++i) { xs[i] = x[s + i]; hgs[i] = hg[s + i]; }
       const int vs = (w.valid - kLanes * s) < 0 ? 0 : (w.valid - kLanes * s);   // live texels of this sub-group
+      // grad_out / target of the light being shaded.  The per-light images are the only global loads inside
+      // the light loop; at 12 warps per SM a plain load (even one light ahead in registers) leaves ~1.3 MB in
+      // flight chip-wide, i.e. ~1.2 TB/s - the fused fit step then waits for them a quarter of its time
+      // (profiles/).  So every thread runs its own cp.async (LDGSTS) ring in shared memory, kRing - 1 lights
+      // ahead: no registers, no cross-thread synchronisation (a thread only ever reads what it copied).
+      constexpr int NT = kLanes * G;
+      float* ring = s_ring + tid * NT;   // [slot][channel][thread][NT]
+      const int nl_src = p.flags.per_light ? p.flags.L : 1;
+      auto issue = [&](int l) {
+        if (l < nl_src) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float* src = p.gsrc.ptr + plane_off(p.gsrc, b, c, w.row, w.col0 + kLanes * s) + (int64_t)l * p.gsrc_sl;
+            float* dst = ring + ((l % kRing) * 3 + c) * (kCtThreads * NT);
+            if (NT == 2 && w.vec) {
+              cp_async8(dst, src);
+            } else {
+#pragma unroll
+              for (int i = 0; i < NT; ++i) cp_async4(dst + i, src + (i < vs ? i : (vs > 0 ? vs - 1 : 0)));
+            }
+          }
+        }
+        cp_async_commit();   // always: keeps the group count uniform
+      };
+      auto fetch = [&](int l) {
+        if (l == 0) {
+#pragma unroll
+          for (int q = 0; q < kRing - 1; ++q) issue(q);
+        } else {
+          issue(l + kRing - 2);
+        }
+      };
+      float t_cur[3][NT];
+      auto take = [&](int l) {   // light l has landed once at most kRing - 1 younger groups are pending
+        cp_async_wait<kRing - 1>();
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int i = 0; i < NT; ++i) t_cur[c][i] = ring[((l % kRing) * 3 + c) * (kCtThreads * NT) + i];
+      };
       auto gout = [&](int l, const V(&outv)[3][G], V(&g)[3][G]) {
+        take(l);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          float tv[kLanes * G], ov[kLanes * G], gv[kLanes * G];
-          load_seg<kLanes * G>(p.gsrc.ptr + plane_off(p.gsrc, b, c, w.row, w.col0 + kLanes * s) + (int64_t)l * p.gsrc_sl, w.vec, vs, tv);
+          float ov[kLanes * G], gv[kLanes * G];
           unpair_to<G>(outv[c], 0, ov);
 #pragma unroll
           for (int i = 0; i < kLanes * G; ++i) {
             if (is_loss) {
-              float diff = (i < vs) ? ov[i] - tv[i] : 0.0f;
+              float diff = (i < vs) ? ov[i] - t_cur[c][i] : 0.0f;
               loss_local += diff * diff;
               gv[i] = 2.0f * p.loss_scale * diff;
             } else {
-              gv[i] = (i < vs) ? tv[i] : 0.0f;
+              gv[i] = (i < vs) ? t_cur[c][i] : 0.0f;
             }
           }
           pairs_of<G>(gv, 0, g[c]);
@@ -354,7 +414,7 @@ __global__ void __launch_bounds__(kCtThreads, PBR_BWD_MIN_CTAS) ct_backward_kern
         }
       };
       V da[3][G], dn[3][G], dr[G], dm[3][G];
-      ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm);
+      ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch);
 #pragma unroll
       for (int c = 0; c < 3; ++c) { unpair_to<G>(da[c], s, d_albedo[c]); unpair_to<G>(dn[c], s, d_normal[c]); unpair_to<G>(dm[c], s, d_met[c]); }
       unpair_to<G>(dr, s, d_rough);
@@ -362,17 +422,17 @@ __global__ void __launch_bounds__(kCtThreads, PBR_BWD_MIN_CTAS) ct_backward_kern
     if (w.active) {
       if (p.d_albedo.ptr) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) store_seg<kTexels>(p.d_albedo.ptr + plane_off(p.d_albedo, b, c, w.row, w.col0), w.vec, w.valid, d_albedo[c]);
+        for (int c = 0; c < 3; ++c) store_seg<kCtTexels>(p.d_albedo.ptr + plane_off(p.d_albedo, b, c, w.row, w.col0), w.vec, w.valid, d_albedo[c]);
       }
       if (p.normal.ptr && p.d_normal.ptr) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) store_seg<kTexels>(p.d_normal.ptr + plane_off(p.d_normal, b, c, w.row, w.col0), w.vec, w.valid, d_normal[c]);
+        for (int c = 0; c < 3; ++c) store_seg<kCtTexels>(p.d_normal.ptr + plane_off(p.d_normal, b, c, w.row, w.col0), w.vec, w.valid, d_normal[c]);
       }
-      if (p.d_roughness.ptr) store_seg<kTexels>(p.d_roughness.ptr + plane_off(p.d_roughness, b, 0, w.row, w.col0), w.vec, w.valid, d_rough);
+      if (p.d_roughness.ptr) store_seg<kCtTexels>(p.d_roughness.ptr + plane_off(p.d_roughness, b, 0, w.row, w.col0), w.vec, w.valid, d_rough);
       if (p.d_metspec.ptr) {
         constexpr int mc = WF == 0 ? 1 : 3;
 #pragma unroll
-        for (int c = 0; c < mc; ++c) store_seg<kTexels>(p.d_metspec.ptr + plane_off(p.d_metspec, b, c, w.row, w.col0), w.vec, w.valid, d_met[c]);
+        for (int c = 0; c < mc; ++c) store_seg<kCtTexels>(p.d_metspec.ptr + plane_off(p.d_metspec, b, c, w.row, w.col0), w.vec, w.valid, d_met[c]);
       }
     }
   }
@@ -595,9 +655,9 @@ static bool plane_vec_ok(const PbrPlane& pl) {
 }
 
 // A CTA of `threads` threads covers a strip of up to 256 texels of blockDim.y consecutive rows.
-static void launch_shape(int B, int H, int W, dim3& grid, dim3& block, int threads = kThreads) {
-  const int max_bx = 256 / kTexels < threads ? 256 / kTexels : threads;
-  int groups = (W + kTexels - 1) / kTexels;
+static void launch_shape(int B, int H, int W, dim3& grid, dim3& block, int threads = kThreads, int texels = kTexels) {
+  const int max_bx = 256 / texels < threads ? 256 / texels : threads;
+  int groups = (W + texels - 1) / texels;
   int bx = 1;
   while (bx < groups && bx < max_bx) bx <<= 1;
   int by = threads / bx;
@@ -605,7 +665,7 @@ static void launch_shape(int B, int H, int W, dim3& grid, dim3& block, int threa
   grid = dim3((groups + bx - 1) / bx, (H + by - 1) / by, B);
 }
 // smallest blockDim.y any kernel is launched with
-constexpr int kMinBy = ((kCtThreads < kThreads ? kCtThreads : kThreads) * kTexels) / 256 > 0 ? ((kCtThreads < kThreads ? kCtThreads : kThreads) * kTexels) / 256 : 1;
+constexpr int kMinBy = 1;
 
 static int check_dims(int B, int H, int W) {
   if (B < 1 || H < 1 || W < 1 || B > 65535 || H > 65535 * kMinBy) return PBR_E_SHAPE;  // grid.z = ceil(B / mats), grid.y = ceil(H / blockDim.y), blockDim.y >= kMinBy
@@ -661,7 +721,7 @@ static int light_mode(const CtKParams& k) {
 }
 
 static void ct_launch_shape(CtKParams& k, dim3& grid, dim3& block) {
-  launch_shape(k.B, k.H, k.W, grid, block, kCtThreads);
+  launch_shape(k.B, k.H, k.W, grid, block, kCtThreads, kCtTexels);
   k.mats_per_cta = (light_mode(k) == kLightPointHoisted) ? (k.B < kHoistMats ? k.B : kHoistMats) : 1;
   grid.z = (k.B + k.mats_per_cta - 1) / k.mats_per_cta;
 }
@@ -712,7 +772,7 @@ static bool fits_i32(const PbrPlane& pl, int H, int W) {
 }
 
 static bool stream_shape(const CtKParams& k, dim3& grid, dim3& block, int& mats) {
-  if (stream_disabled() || k.force_generic || k.flags.L != 1 || !k.vec_ok || (k.W % 4) != 0 || kTexels != 4) return false;
+  if (stream_disabled() || k.force_generic || k.flags.L != 1 || !k.vec_ok || (k.W % 4) != 0) return false;
   static const int min_bx = [] { const char* e = getenv("PBR_STREAM_MIN_BX"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
   int groups = k.W / kST, bx = min_bx < 4 / kST ? 4 / kST : min_bx;   // a row segment is a multiple of 16 bytes
   while (bx < groups && bx < kStreamThreads) bx <<= 1;

@@ -148,14 +148,21 @@ PBR_HD void ct_forward_group(const CtStage& S, const CtFlags& F, const V (&araw)
 //   gout(l, out[3][N], g[3][N]) : given the encoded output of light l (or of the accumulated image,
 //        l = 0) fills g = dLoss/d out.  The plain backward ignores `out` and loads grad_out; the fused
 //        loss kernel computes 2*scale*(out - target) and accumulates the loss.
+//   fetch(l)                    : software prefetch hook of the generic kernels: "what was fetched last becomes
+//        current, start loading the grad_out / target of light l" (l == L: rotate only).  gout(l) then reads the
+//        current buffer, which was requested one whole light iteration earlier.
 //   int_sink(l, g_int[3])       : per-light intensity gradient summed over the texels of the group.
 // Results: d_albedo/d_normal/d_met [3][N], d_rough[N].
 // ------------------------------------------------------------------------------------------------
-template <int kWorkflow, int kLight, class V, int N, class Gout, class IntSink>
+struct NoFetch {
+  PBR_HD void operator()(int) const {}
+};
+
+template <int kWorkflow, int kLight, class V, int N, class Gout, class IntSink, class Fetch = NoFetch>
 PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw)[3][N], const V (&nraw)[3][N],
                               const V (&rough)[N], const V (&mraw)[3][N], const V (&x)[N], float y,
                               const LightGeomT<V> (&hoisted)[N], Gout gout, IntSink int_sink, V (&d_albedo)[3][N],
-                              V (&d_normal)[3][N], V (&d_rough)[N], V (&d_met)[3][N]) {
+                              V (&d_normal)[3][N], V (&d_rough)[N], V (&d_met)[3][N], Fetch fetch = Fetch()) {
   Texel<kWorkflow, V> t[N];
   TexelGrad<V> tg[N];
 #pragma unroll
@@ -170,6 +177,7 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
   const int L = (kLight == kLightPointHoisted) ? 1 : F.L;
   const bool two_pass = (!F.per_light) && L > 1;
   V g_tot[3][N];  // two-pass only: gradient w.r.t. every per-light colour
+  fetch(0);
   if (two_pass) {
     // pass 1: the accumulated image, to know where clamp(sum) gates and the slope of the encode
     V acc[3][N];
@@ -198,6 +206,7 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
         outv[c][i] = encode_out_d(cl, F.return_srgb, &slope[c][i]);
         slope[c][i] = gated(slope[c][i], acc[c][i], cl);
       }
+    fetch(L);   // rotate: the buffer requested before pass 1 becomes current
     gout(0, outv, g_tot);
 #pragma unroll
     for (int c = 0; c < 3; ++c)
@@ -206,6 +215,7 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
   }
 
   for (int l = 0; l < L; ++l) {
+    if (!two_pass) fetch(l + 1);   // light l becomes current, light l + 1 is requested
     LightGeomT<V> g[N];
     LightFwd<V> f[N];
     V outv[3][N], slope[3][N], gl[3][N];

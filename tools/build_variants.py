@@ -14,16 +14,17 @@ def v(**kw):
 
 
 VARIANTS = {
-    "scalar": ["-DPBR_SCALAR_LANES", "-DPBR_FWD_GROUP=2", "-DPBR_CT_THREADS=256", "-DPBR_FWD_MIN_CTAS=3", "-DPBR_BWD_MIN_CTAS=2",
+    "scalar": ["-DPBR_SCALAR_LANES", "-DPBR_FWD_GROUP=2", "-DPBR_CT_THREADS=256", "-DPBR_CT_TEXELS=4", "-DPBR_FWD_MIN_CTAS=3", "-DPBR_BWD_MIN_CTAS=2",
                "-DPBR_STREAM_THREADS=256", "-DPBR_STREAM_FWD_MIN_CTAS=2", "-DPBR_STREAM_BWD_MIN_CTAS=2"],   # one texel per lane (V = float): accuracy / speed reference
     "default": [],
-    "t128x4_f4b3_s3": v(stream_stages=3),
-    "t128x4_f4b4": v(stream_bwd_min_ctas=4),
-    "t128x4_f3b3": v(stream_fwd_min_ctas=3),
-    "t256x4_f2b2": v(stream_threads=256, stream_fwd_min_ctas=2, stream_bwd_min_ctas=2),
-    "t256x2_f3b2": v(stream_threads=256, stream_texels=2, stream_fwd_min_ctas=3, stream_bwd_min_ctas=2),
-    "t128x2_f6b4": v(stream_texels=2, stream_fwd_min_ctas=6, stream_bwd_min_ctas=4),
-    "t64x4_f8b6": v(stream_threads=64, stream_fwd_min_ctas=8, stream_bwd_min_ctas=6),
+    # generic (multi-light) kernels: threads per CTA / texels per thread / CTAs per SM (register cap)
+    "g_t128x2_f5b4": v(fwd_min_ctas=5, bwd_min_ctas=4),
+    "g_t128x2_f4b2": v(fwd_min_ctas=4, bwd_min_ctas=2),
+    "g_t128x4_f4b3": v(ct_texels=4),
+    "g_t256x2_f2b2": v(ct_threads=256, fwd_min_ctas=2, bwd_min_ctas=2),
+    "g_t256x2_f3b1": v(ct_threads=256, fwd_min_ctas=3, bwd_min_ctas=1),
+    "g_t64x2_f8b6": v(ct_threads=64, fwd_min_ctas=8, bwd_min_ctas=6),
+    "g_t64x2_f10b5": v(ct_threads=64, fwd_min_ctas=10, bwd_min_ctas=5),
     # memory pipeline only (no shading math): the floor of the TMA-in / STG-out design
     "nomath": ["-DPBR_DBG_NOMATH"],
 }

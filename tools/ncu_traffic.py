@@ -1,0 +1,22 @@
+"""Write profiles/traffic.json: per-launch DRAM bytes of the dominant kernels from `ncu --page raw --csv` dumps.
+usage: python tools/ncu_traffic.py c2=gpurun_out/prof_c2.raw.csv c3=gpurun_out/prof_c3.raw.csv ..."""
+import csv, json, os, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+out_path = os.path.join(ROOT, "profiles", "traffic.json")
+out = json.load(open(out_path)) if os.path.exists(out_path) else {}
+for arg in sys.argv[1:]:
+    cfg, path = arg.split("=")
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    for r in rows[2:]:
+        name = r[col["Kernel Name"]]
+        rd = float(r[col["dram__bytes_read.sum"]]) * UNIT[units[col["dram__bytes_read.sum"]]]
+        wr = float(r[col["dram__bytes_write.sum"]]) * UNIT[units[col["dram__bytes_write.sum"]]]
+        kind = "backward" if "backward" in name else ("forward" if "forward" in name else name.split("(")[0].replace("void ", ""))
+        out[f"{cfg}:{kind}"] = {"kernel": name, "bytes": rd + wr, "read": rd, "write": wr,
+                                "source": f"ncu --set full, {os.path.basename(path)} (profiles/)"}
+json.dump(out, open(out_path, "w"), indent=1)
+print(json.dumps(out, indent=1))

@@ -32,8 +32,9 @@ def padded(t):
 
 
 maps = {k: padded(v) for k, v in synth_maps(B, H, W, dev, 3).items()}
-out = padded(torch.empty(B, 3, H, W, device=dev))
-go = padded(torch.rand(B, 3, H, W, device=dev))
+PER_LIGHT_SHAPE = (B, L, 3, H, W) if int(os.environ.get("TUNE_PER_LIGHT", 0)) else (B, 3, H, W)
+out = torch.empty(PER_LIGHT_SHAPE, device=dev) if len(PER_LIGHT_SHAPE) == 5 else padded(torch.empty(B, 3, H, W, device=dev))
+go = torch.rand(PER_LIGHT_SHAPE, device=dev) if len(PER_LIGHT_SHAPE) == 5 else padded(torch.rand(B, 3, H, W, device=dev))
 grads = {k: padded(torch.empty_like(v)) for k, v in maps.items()}
 import math
 if L == 1:
@@ -45,14 +46,20 @@ hv, hl, hi = _cabi.host_floats([0.0, 0.0, 1.0]), _cabi.host_floats(lights), _cab
 
 d = _cabi.PbrCtDesc()
 d.B, d.H, d.W, d.L = B, H, W, L
-d.workflow, d.light_type, d.albedo_is_srgb, d.specular_is_srgb, d.return_srgb, d.per_light = 0, 1, 1, 1, 1, 0
+PER_LIGHT = int(os.environ.get("TUNE_PER_LIGHT", 0))   # 1: (B,L,3,H,W) output / target, the fused-loss entry point is timed as "bwd"
+d.workflow, d.light_type, d.albedo_is_srgb, d.specular_is_srgb, d.return_srgb, d.per_light = 0, 1, 1, 1, 1, PER_LIGHT
 d.light_size = 1.0
 d.metallic_channels = 1
 d.albedo, d.normal, d.roughness, d.metspec = (_cabi.plane(maps[k]) for k in ("albedo", "normal", "roughness", "metallic"))
 d.view, d.lights, d.intensity = (ctypes.cast(x, ctypes.c_void_p) for x in (hv, hl, hi))
-d.out, d.out_sl = _out_plane(out, False, True)
+d.out, d.out_sl = _out_plane(out, bool(PER_LIGHT), True)
 g = _cabi.PbrCtGrads()
-g.grad_out, g.grad_out_sl = _out_plane(go, False, True)
+g.grad_out, g.grad_out_sl = _out_plane(go, bool(PER_LIGHT), True)
+loss_buf = torch.zeros(1, device=dev)
+ls = _cabi.PbrCtLoss()
+ls.target, ls.target_sl = _out_plane(go, bool(PER_LIGHT), True)
+ls.loss_scale = 1.0 / go.numel()
+ls.loss_sum = loss_buf.data_ptr()
 g.d_albedo, g.d_normal, g.d_roughness, g.d_metspec = (_cabi.plane(grads[k]) for k in ("albedo", "normal", "roughness", "metallic"))
 
 stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -70,13 +77,19 @@ for path in paths:
         fn.restype = ctypes.c_int
     lib.pbr_ct_forward.argtypes = [ctypes.POINTER(_cabi.PbrCtDesc), ctypes.c_void_p]
     lib.pbr_ct_backward.argtypes = [ctypes.POINTER(_cabi.PbrCtDesc), ctypes.POINTER(_cabi.PbrCtGrads), ctypes.c_void_p]
+    lib.pbr_ct_loss_fwd_bwd.restype = ctypes.c_int
+    lib.pbr_ct_loss_fwd_bwd.argtypes = [ctypes.POINTER(_cabi.PbrCtDesc), ctypes.POINTER(_cabi.PbrCtLoss),
+                                        ctypes.POINTER(_cabi.PbrCtGrads), ctypes.c_void_p]
 
     def fwd():
         rc = lib.pbr_ct_forward(ctypes.byref(d), stream)
         assert rc == 0, rc
 
     def bwd():
-        rc = lib.pbr_ct_backward(ctypes.byref(d), ctypes.byref(g), stream)
+        if PER_LIGHT:
+            rc = lib.pbr_ct_loss_fwd_bwd(ctypes.byref(d), ctypes.byref(ls), ctypes.byref(g), stream)
+        else:
+            rc = lib.pbr_ct_backward(ctypes.byref(d), ctypes.byref(g), stream)
         assert rc == 0, rc
 
     times = {}
