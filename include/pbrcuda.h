@@ -27,9 +27,11 @@
 extern "C" {
 #endif
 
-#define PBR_ABI_VERSION 2
+#define PBR_ABI_VERSION 3
 #define PBR_MAX_LIGHTS 64      /* lights per launch (parameters are staged in shared memory) */
 #define PBR_MAX_BLEND_MAPS 12  /* maps blended by one pbr_blend launch */
+#define PBR_MAX_INDEX_MAPS 12  /* maps moved by one pbr_index_transform launch */
+#define PBR_MAX_ADAM_MAPS 8    /* parameter maps updated by one pbr_adam_step launch */
 
 /* error codes (negative) */
 #define PBR_OK 0
@@ -167,6 +169,70 @@ typedef struct PbrNormalDesc {
   PbrPlane in, out;
 } PbrNormalDesc;
 
+/*
+ * Image ingestion - the step before the shading path.  Replaces
+ * MaterialBase._to_tensor for 8/16-bit images (pypbr/materials/base.py:122-168: TF.to_tensor divides by 255,
+ * 16-bit by 65535) fused with MaterialBase._process_normal_map (base.py:191-242) for normal maps, so a material
+ * travels host -> device as 8 (or 16) bit texels instead of float32.
+ *   src: DEVICE pointer to an interleaved image (H, W, src_channels) of uint8 (bits = 8) or uint16 (bits = 16);
+ *        strides in BYTES; out receives the first `channels` channels (PLAIN) or 3 channels (NORMAL2/3).
+ */
+enum { PBR_INGEST_PLAIN = 0, PBR_INGEST_NORMAL3 = 1, PBR_INGEST_NORMAL2 = 2 };
+typedef struct PbrIngestDesc {
+  int32_t B, H, W;
+  int32_t bits;             /* 8 or 16 */
+  int32_t src_channels;     /* interleaved channels per pixel in src (1..4) */
+  int32_t channels;         /* PLAIN: channels to extract (1..4, <= src_channels) */
+  int32_t mode;             /* PBR_INGEST_* */
+  const void* src;
+  int64_t src_batch_stride, src_row_stride;   /* bytes */
+  PbrPlane out;
+} PbrIngestDesc;
+
+/*
+ * Index transforms of every map of a material in one pass.  Replaces the per-map
+ * tensor.flip / torch.roll / tensor.repeat / TF.crop calls of MaterialBase.flip_horizontal, flip_vertical, roll,
+ * tile and crop (pypbr/materials/base.py:490-537, 605-655), including the sign flip of the normal's x / y.
+ *   out[c, y, x] = sign_c * in[c, origin_y + step_y*y, origin_x + step_x*x]; indices are wrapped modulo the input
+ *   size when `wrap`, otherwise texels that fall outside the input are 0 (TF.crop zero-pads).  Pure data movement:
+ *   results are bit-identical to the reference's torch calls.
+ */
+typedef struct PbrIndexMap {
+  PbrPlane in, out;
+  int32_t channels;         /* 1..4 */
+  int32_t negate_mask;      /* bit c set: channel c changes sign (normal x for a horizontal flip, y for a vertical one) */
+} PbrIndexMap;
+typedef struct PbrIndexDesc {
+  int32_t B, H_in, W_in, H_out, W_out;
+  int32_t origin_y, step_y, origin_x, step_x;
+  int32_t wrap;
+  int32_t n_maps;
+  PbrIndexMap maps[PBR_MAX_INDEX_MAPS];
+} PbrIndexDesc;
+
+/*
+ * Adam step + projection of every parameter map of the inverse-rendering fit in one pass - the step after the
+ * shading path.  No reference code exists (docs/source/tutorials/06_advanced.rst:136-137
+ * leaves the optimiser to the reader); the update is torch.optim.Adam's:
+ *   m = m + (1-beta1)(g - m); v = beta2 v + (1-beta2) g^2; p -= step_size * m / (sqrt(v)/bias2_sqrt + eps)
+ * with g = grad * grad_scale, step_size = lr / (1 - beta1^t), bias2_sqrt = sqrt(1 - beta2^t) computed by the caller.
+ * Projection keeps the maps valid: CLAMP to [lo, hi] (albedo, roughness, metallic, specular), NORMALIZE the 3-vector
+ * (normal).  param / exp_avg / exp_avg_sq are updated in place.
+ */
+enum { PBR_PROJECT_NONE = 0, PBR_PROJECT_CLAMP = 1, PBR_PROJECT_NORMALIZE = 2 };
+typedef struct PbrAdamMap {
+  PbrPlane param, grad, exp_avg, exp_avg_sq;
+  int32_t channels;         /* 1..4; NORMALIZE requires 3 */
+  int32_t project;          /* PBR_PROJECT_* */
+  float lo, hi;
+} PbrAdamMap;
+typedef struct PbrAdamDesc {
+  int32_t B, H, W;
+  int32_t n_maps;
+  float step_size, one_minus_beta1, beta2, one_minus_beta2, bias2_sqrt, eps, grad_scale;
+  PbrAdamMap maps[PBR_MAX_ADAM_MAPS];
+} PbrAdamDesc;
+
 int pbr_abi_version(void);
 const char* pbr_strerror(int code);
 
@@ -180,10 +246,14 @@ int pbr_blend(const PbrBlendDesc* desc, pbr_stream_t stream);
 int pbr_color_convert(const PbrColorDesc* desc, pbr_stream_t stream);
 int pbr_normal_min(const PbrNormalDesc* desc, float* result, pbr_stream_t stream);
 int pbr_normal_ingest(const PbrNormalDesc* desc, pbr_stream_t stream);
+int pbr_ingest_image(const PbrIngestDesc* desc, pbr_stream_t stream);
+int pbr_index_transform(const PbrIndexDesc* desc, pbr_stream_t stream);
+int pbr_adam_step(const PbrAdamDesc* desc, pbr_stream_t stream);
 
 /* sizeof() of the descriptor structs as THIS library was compiled (binding self-check):
    which = 0 PbrPlane, 1 PbrCtDesc, 2 PbrCtGrads, 3 PbrCtLoss, 4 PbrConvDesc, 5 PbrBlendMap, 6 PbrBlendDesc,
-   7 PbrColorDesc, 8 PbrNormalDesc; anything else returns 0. */
+   7 PbrColorDesc, 8 PbrNormalDesc, 9 PbrIngestDesc, 10 PbrIndexMap, 11 PbrIndexDesc, 12 PbrAdamMap, 13 PbrAdamDesc;
+   anything else returns 0. */
 uint64_t pbr_sizeof(int which);
 
 /* Number of kernel launches this process has enqueued through the library (for bench accounting). */

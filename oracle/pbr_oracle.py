@@ -307,3 +307,85 @@ def rendering_loss(pred_maps, target_render: Tensor, view_dir, lights, intensiti
     """mean((render(pred) - target)^2) over every element, per-light mode for L > 1."""
     out = render(pred_maps, view_dir, lights, intensities, accumulate=False, **kw)
     return ((out - target_render) ** 2).mean()
+
+
+# --------------------------------------------------------------------------------------
+# SURVEY.md §8f "next" rows: ingestion, index transforms, optimiser step
+# --------------------------------------------------------------------------------------
+
+
+def ingest_image(arr, is_normal: bool = False) -> Tensor:
+    """
+    MaterialBase._to_tensor for a PIL-style array (pypbr/materials/base.py:122-168): uint8 (H,W[,C]) ->
+    TF.to_tensor == permute + float32 / 255; uint16 (H,W) -> float32 / 65535 with a leading channel;
+    then, for a normal map, process_normal_map above (base.py:191-242).
+    """
+    t = torch.as_tensor(arr)
+    if t.dtype == torch.uint8:
+        if t.dim() == 2:
+            t = t.unsqueeze(-1)
+        out = t.permute(2, 0, 1).contiguous().to(torch.float32).div(255)   # torchvision F.to_tensor
+    else:
+        out = (torch.as_tensor(arr.astype("float32")).unsqueeze(0) / 65535.0)
+    return process_normal_map(out) if is_normal else out
+
+
+def flip_horizontal(maps: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    """pypbr/materials/base.py:605-621."""
+    out = {}
+    for name, t in maps.items():
+        f = t.flip(-1)
+        if name == "normal":
+            f = f.clone()
+            f[0] = -f[0]
+        out[name] = f
+    return out
+
+
+def flip_vertical(maps: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    """pypbr/materials/base.py:623-639."""
+    out = {}
+    for name, t in maps.items():
+        f = t.flip(-2)
+        if name == "normal":
+            f = f.clone()
+            f[1] = -f[1]
+        out[name] = f
+    return out
+
+
+def roll(maps: Dict[str, Tensor], shift) -> Dict[str, Tensor]:
+    """pypbr/materials/base.py:641-655."""
+    return {k: torch.roll(t, shift, dims=(1, 2)) for k, t in maps.items()}
+
+
+def tile(maps: Dict[str, Tensor], n: int) -> Dict[str, Tensor]:
+    """pypbr/materials/base.py:521-537."""
+    return {k: t.repeat(1, n, n) for k, t in maps.items()}
+
+
+def adam_fit_steps(params: Dict[str, Tensor], grads_per_step, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, projection=None):
+    """
+    The optimiser of the inverse-rendering fit.  The reference stops at "Perform backpropagation and optimization
+    steps here" (docs/source/tutorials/06_advanced.rst:136-137); the checker is torch.optim.Adam itself
+    (single-tensor path) followed by the projection onto the valid range after every step:
+    clamp(0, 1) for colour / scalar maps, F.normalize(dim=channel) for the normal map.
+    grads_per_step: list of dicts name -> gradient.  Returns the parameters after the last step.
+    """
+    import torch.nn.functional as F
+
+    projection = projection or {}
+    ps = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    opt = torch.optim.Adam(list(ps.values()), lr=lr, betas=betas, eps=eps, foreach=False, fused=False)
+    for grads in grads_per_step:
+        for k, p in ps.items():
+            p.grad = grads[k].clone()
+        opt.step()
+        with torch.no_grad():
+            for k, p in ps.items():
+                kind = projection.get(k, "normalize" if k == "normal" else "clamp")
+                if kind == "clamp":
+                    p.clamp_(0.0, 1.0)
+                elif kind == "normalize":
+                    p.copy_(F.normalize(p, dim=p.dim() - 3))
+    return {k: v.detach() for k, v in ps.items()}

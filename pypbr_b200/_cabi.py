@@ -16,13 +16,17 @@ from typing import Optional, Sequence
 
 import torch
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 PBR_MAX_LIGHTS = 64
 PBR_MAX_BLEND_MAPS = 12
+PBR_MAX_INDEX_MAPS = 12
+PBR_MAX_ADAM_MAPS = 8
 
 WORKFLOW_METALLIC, WORKFLOW_SPECULAR = 0, 1
 LIGHT_DIRECTIONAL, LIGHT_POINT = 0, 1
 MASK_GIVEN, MASK_SIGMOID, MASK_GRADIENT_H, MASK_GRADIENT_V = 0, 1, 2, 3
+INGEST_PLAIN, INGEST_NORMAL3, INGEST_NORMAL2 = 0, 1, 2
+PROJECT_NONE, PROJECT_CLAMP, PROJECT_NORMALIZE = 0, 1, 2
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libpbrcuda.so")
 
@@ -90,8 +94,47 @@ class PbrNormalDesc(Structure):
     _fields_ = [("B", c_int32), ("H", c_int32), ("W", c_int32), ("channels", c_int32), ("in_", PbrPlane), ("out", PbrPlane)]
 
 
+class PbrIngestDesc(Structure):
+    _fields_ = [
+        ("B", c_int32), ("H", c_int32), ("W", c_int32), ("bits", c_int32), ("src_channels", c_int32),
+        ("channels", c_int32), ("mode", c_int32),
+        ("src", c_void_p), ("src_batch_stride", c_int64), ("src_row_stride", c_int64),
+        ("out", PbrPlane),
+    ]
+
+
+class PbrIndexMap(Structure):
+    _fields_ = [("in_", PbrPlane), ("out", PbrPlane), ("channels", c_int32), ("negate_mask", c_int32)]
+
+
+class PbrIndexDesc(Structure):
+    _fields_ = [
+        ("B", c_int32), ("H_in", c_int32), ("W_in", c_int32), ("H_out", c_int32), ("W_out", c_int32),
+        ("origin_y", c_int32), ("step_y", c_int32), ("origin_x", c_int32), ("step_x", c_int32),
+        ("wrap", c_int32), ("n_maps", c_int32),
+        ("maps", PbrIndexMap * PBR_MAX_INDEX_MAPS),
+    ]
+
+
+class PbrAdamMap(Structure):
+    _fields_ = [
+        ("param", PbrPlane), ("grad", PbrPlane), ("exp_avg", PbrPlane), ("exp_avg_sq", PbrPlane),
+        ("channels", c_int32), ("project", c_int32), ("lo", c_float), ("hi", c_float),
+    ]
+
+
+class PbrAdamDesc(Structure):
+    _fields_ = [
+        ("B", c_int32), ("H", c_int32), ("W", c_int32), ("n_maps", c_int32),
+        ("step_size", c_float), ("one_minus_beta1", c_float), ("beta2", c_float), ("one_minus_beta2", c_float),
+        ("bias2_sqrt", c_float), ("eps", c_float), ("grad_scale", c_float),
+        ("maps", PbrAdamMap * PBR_MAX_ADAM_MAPS),
+    ]
+
+
 # order = the `which` argument of pbr_sizeof()
-STRUCTS = (PbrPlane, PbrCtDesc, PbrCtGrads, PbrCtLoss, PbrConvDesc, PbrBlendMap, PbrBlendDesc, PbrColorDesc, PbrNormalDesc)
+STRUCTS = (PbrPlane, PbrCtDesc, PbrCtGrads, PbrCtLoss, PbrConvDesc, PbrBlendMap, PbrBlendDesc, PbrColorDesc, PbrNormalDesc,
+           PbrIngestDesc, PbrIndexMap, PbrIndexDesc, PbrAdamMap, PbrAdamDesc)
 
 _lib = None
 
@@ -99,7 +142,7 @@ _lib = None
 EXPORTS = (
     "pbr_abi_version", "pbr_strerror", "pbr_ct_forward", "pbr_ct_backward", "pbr_ct_loss_fwd_bwd",
     "pbr_convert_m2s", "pbr_convert_s2m", "pbr_blend", "pbr_color_convert", "pbr_normal_min",
-    "pbr_normal_ingest", "pbr_launch_count", "pbr_sizeof",
+    "pbr_normal_ingest", "pbr_ingest_image", "pbr_index_transform", "pbr_adam_step", "pbr_launch_count", "pbr_sizeof",
 )
 
 
@@ -134,6 +177,9 @@ def load():
     lib.pbr_color_convert.argtypes = [POINTER(PbrColorDesc), c_void_p]
     lib.pbr_normal_min.argtypes = [POINTER(PbrNormalDesc), c_void_p, c_void_p]
     lib.pbr_normal_ingest.argtypes = [POINTER(PbrNormalDesc), c_void_p]
+    lib.pbr_ingest_image.argtypes = [POINTER(PbrIngestDesc), c_void_p]
+    lib.pbr_index_transform.argtypes = [POINTER(PbrIndexDesc), c_void_p]
+    lib.pbr_adam_step.argtypes = [POINTER(PbrAdamDesc), c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("pbr_strerror", "pbr_launch_count", "pbr_sizeof"):

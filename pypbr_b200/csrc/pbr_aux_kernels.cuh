@@ -1,0 +1,197 @@
+// pbr_aux_kernels.cuh — the streaming kernels either side of the shading path:
+//   ingest_kernel          : 8/16-bit interleaved image -> float32 planar map, with the normal-map remap
+//                            (the step BEFORE the path: MaterialBase._to_tensor + _process_normal_map)
+//   index_transform_kernel : flip / roll / tile / crop of every map of a material in one pass, with the
+//                            normal's sign flips (MaterialBase.flip_horizontal ... crop)
+//   adam_kernel            : Adam update of every parameter map of the fit + projection onto the valid
+//                            range (the step AFTER the path: the optimiser of the inverse-rendering fit)
+// All HBM-bound: one thread owns kTexels consecutive texels of a row, 128-bit accesses where the
+// layout allows.  Included by pbr_kernels.cu (uses its Where / load_seg / store_seg helpers).
+#pragma once
+
+namespace pbr {
+
+// ------------------------------------------------------------------------------------------------
+// ingestion: pypbr/materials/base.py:122-168 (TF.to_tensor: /255; 16-bit: /65535) + :191-242
+// ------------------------------------------------------------------------------------------------
+struct IngestKParams {
+  PbrIngestDesc d;
+  int vec_ok;
+};
+
+__device__ __forceinline__ unsigned ingest_raw(const PbrIngestDesc& d, int b, int row, int col, int c) {
+  const unsigned char* base = static_cast<const unsigned char*>(d.src) + (int64_t)b * d.src_batch_stride + (int64_t)row * d.src_row_stride;
+  if (d.bits == 8) return base[(int64_t)col * d.src_channels + c];
+  return reinterpret_cast<const unsigned short*>(base)[(int64_t)col * d.src_channels + c];
+}
+
+__global__ void __launch_bounds__(kThreads) ingest_kernel(const __grid_constant__ IngestKParams p) {
+  const PbrIngestDesc& d = p.d;
+  // x / 255 for every byte value, computed once per CTA with the IEEE division torch uses: exact by construction
+  __shared__ float lut[256];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (d.bits == 8)
+    for (int i = tid; i < 256; i += kThreads) lut[i] = xdiv((float)i, 255.0f);
+  __syncthreads();
+  const Where w = locate(d.H, d.W, p.vec_ok != 0);
+  if (!w.active) return;
+  const int cin = d.mode == PBR_INGEST_NORMAL2 ? 2 : (d.mode == PBR_INGEST_NORMAL3 ? 3 : d.channels);
+  float v[3][kTexels], o[3][kTexels];
+  for (int c = 0; c < cin && c < 3; ++c)
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i) {
+      const int col = w.col0 + (i < w.valid ? i : w.valid - 1);
+      const unsigned raw = ingest_raw(d, w.b, w.row, col, c);
+      v[c][i] = d.bits == 8 ? lut[raw] : xdiv((float)raw, 65535.0f);
+    }
+  if (d.mode == PBR_INGEST_PLAIN) {
+    for (int c = 0; c < d.channels; ++c) {
+      if (c >= 3) {  // 4th channel (alpha) of a plain map
+#pragma unroll
+        for (int i = 0; i < kTexels; ++i) {
+          const int col = w.col0 + (i < w.valid ? i : w.valid - 1);
+          const unsigned raw = ingest_raw(d, w.b, w.row, col, c);
+          v[0][i] = d.bits == 8 ? lut[raw] : xdiv((float)raw, 65535.0f);
+        }
+        store_seg<kTexels>(d.out.ptr + plane_off(d.out, w.b, c, w.row, w.col0), w.vec, w.valid, v[0]);
+      } else {
+        store_seg<kTexels>(d.out.ptr + plane_off(d.out, w.b, c, w.row, w.col0), w.vec, w.valid, v[c]);
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < kTexels; ++i) {
+    float o3[3];
+    if (d.mode == PBR_INGEST_NORMAL3) {
+      const float v3[3] = {v[0][i], v[1][i], v[2][i]};
+      ingest_normal3(v3, o3);
+    } else {
+      const float v2[2] = {v[0][i], v[1][i]};
+      ingest_normal2(v2, o3);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c][i] = o3[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) store_seg<kTexels>(d.out.ptr + plane_off(d.out, w.b, c, w.row, w.col0), w.vec, w.valid, o[c]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// index transforms: pypbr/materials/base.py:490-537 (crop, tile), :605-655 (flips, roll)
+//   out[c, y, x] = sign_c * in[c, fy(y), fx(x)],  f(i) = origin + step * i, wrapped into [0, n_in) when `wrap`,
+//   else 0 where it falls outside (TF.crop pads with zeros)
+// ------------------------------------------------------------------------------------------------
+struct IndexKParams {
+  PbrIndexDesc d;
+  int vec_ok;
+};
+
+__device__ __forceinline__ int wrap_index(int i, int n) {
+  i %= n;
+  return i < 0 ? i + n : i;
+}
+
+__global__ void __launch_bounds__(kThreads) index_transform_kernel(const __grid_constant__ IndexKParams p) {
+  const PbrIndexDesc& d = p.d;
+  const Where w = locate(d.H_out, d.W_out, p.vec_ok != 0);
+  if (!w.active) return;
+  int sy = d.origin_y + d.step_y * w.row;
+  bool row_in = true;
+  if (d.wrap) sy = wrap_index(sy, d.H_in);
+  else row_in = sy >= 0 && sy < d.H_in;
+  int sx[kTexels];
+  bool in[kTexels];
+#pragma unroll
+  for (int i = 0; i < kTexels; ++i) {
+    int x = d.origin_x + d.step_x * (w.col0 + i);
+    if (d.wrap) { x = wrap_index(x, d.W_in); in[i] = true; }
+    else in[i] = row_in && x >= 0 && x < d.W_in;
+    sx[i] = in[i] ? x : 0;
+  }
+  if (!row_in) sy = 0;
+  for (int m = 0; m < d.n_maps; ++m) {
+    const PbrIndexMap& im = d.maps[m];
+    for (int c = 0; c < im.channels; ++c) {
+      const float* src = im.in.ptr + plane_off(im.in, w.b, c, sy, 0);
+      const bool neg = (im.negate_mask >> c) & 1;
+      float v[kTexels];
+#pragma unroll
+      for (int i = 0; i < kTexels; ++i) {
+        float t = (i < w.valid && in[i]) ? __ldg(src + sx[i]) : 0.0f;
+        v[i] = neg ? -t : t;
+      }
+      store_seg<kTexels>(im.out.ptr + plane_off(im.out, w.b, c, w.row, w.col0), w.vec, w.valid, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam + projection (no reference code: the tutorial stops at "perform backpropagation and
+// optimization steps here", docs/source/tutorials/06_advanced.rst:136-137).  Same update as
+// torch.optim.Adam (single-tensor path): m = lerp(m, g, 1-b1); v = v*b2 + (1-b2)*g*g;
+// p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps); then clamp to [lo, hi] or renormalise.
+// ------------------------------------------------------------------------------------------------
+struct AdamKParams {
+  PbrAdamDesc d;
+  int vec_ok;
+};
+
+__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, const PbrAdamDesc& d) {
+  m = m + (g - m) * d.one_minus_beta1;
+  v = v * d.beta2 + d.one_minus_beta2 * g * g;
+  const float denom = xdiv(xsqrt(v), d.bias2_sqrt) + d.eps;
+  return p - d.step_size * xdiv(m, denom);
+}
+
+__global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ AdamKParams p) {
+  const PbrAdamDesc& d = p.d;
+  const Where w = locate(d.H, d.W, p.vec_ok != 0);
+  if (!w.active) return;
+  for (int mi = 0; mi < d.n_maps; ++mi) {
+    const PbrAdamMap& am = d.maps[mi];
+    if (am.project == PBR_PROJECT_NORMALIZE) {
+      float pn[3][kTexels];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float pv[kTexels], g[kTexels], m[kTexels], v[kTexels];
+        const int64_t o = plane_off(am.param, w.b, c, w.row, w.col0);
+        load_seg<kTexels>(am.param.ptr + o, w.vec, w.valid, pv);
+        load_seg<kTexels>(am.grad.ptr + plane_off(am.grad, w.b, c, w.row, w.col0), w.vec, w.valid, g);
+        load_seg<kTexels>(am.exp_avg.ptr + plane_off(am.exp_avg, w.b, c, w.row, w.col0), w.vec, w.valid, m);
+        load_seg<kTexels>(am.exp_avg_sq.ptr + plane_off(am.exp_avg_sq, w.b, c, w.row, w.col0), w.vec, w.valid, v);
+#pragma unroll
+        for (int i = 0; i < kTexels; ++i) pn[c][i] = adam_update(pv[i], g[i] * d.grad_scale, m[i], v[i], d);
+        store_seg<kTexels>(am.exp_avg.ptr + plane_off(am.exp_avg, w.b, c, w.row, w.col0), w.vec, w.valid, m);
+        store_seg<kTexels>(am.exp_avg_sq.ptr + plane_off(am.exp_avg_sq, w.b, c, w.row, w.col0), w.vec, w.valid, v);
+      }
+#pragma unroll
+      for (int i = 0; i < kTexels; ++i) {
+        float o3[3];
+        normalize3(pn[0][i], pn[1][i], pn[2][i], o3);   // F.normalize(dim=channel), eps 1e-12
+        pn[0][i] = o3[0]; pn[1][i] = o3[1]; pn[2][i] = o3[2];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) store_seg<kTexels>(am.param.ptr + plane_off(am.param, w.b, c, w.row, w.col0), w.vec, w.valid, pn[c]);
+    } else {
+      for (int c = 0; c < am.channels; ++c) {
+        float pv[kTexels], g[kTexels], m[kTexels], v[kTexels];
+        load_seg<kTexels>(am.param.ptr + plane_off(am.param, w.b, c, w.row, w.col0), w.vec, w.valid, pv);
+        load_seg<kTexels>(am.grad.ptr + plane_off(am.grad, w.b, c, w.row, w.col0), w.vec, w.valid, g);
+        load_seg<kTexels>(am.exp_avg.ptr + plane_off(am.exp_avg, w.b, c, w.row, w.col0), w.vec, w.valid, m);
+        load_seg<kTexels>(am.exp_avg_sq.ptr + plane_off(am.exp_avg_sq, w.b, c, w.row, w.col0), w.vec, w.valid, v);
+#pragma unroll
+        for (int i = 0; i < kTexels; ++i) {
+          float np = adam_update(pv[i], g[i] * d.grad_scale, m[i], v[i], d);
+          if (am.project == PBR_PROJECT_CLAMP) np = fminf(fmaxf(np, am.lo), am.hi);
+          pv[i] = np;
+        }
+        store_seg<kTexels>(am.param.ptr + plane_off(am.param, w.b, c, w.row, w.col0), w.vec, w.valid, pv);
+        store_seg<kTexels>(am.exp_avg.ptr + plane_off(am.exp_avg, w.b, c, w.row, w.col0), w.vec, w.valid, m);
+        store_seg<kTexels>(am.exp_avg_sq.ptr + plane_off(am.exp_avg_sq, w.b, c, w.row, w.col0), w.vec, w.valid, v);
+      }
+    }
+  }
+}
+
+}  // namespace pbr

@@ -644,6 +644,12 @@ __global__ void __launch_bounds__(kThreads) normal_ingest_kernel(const __grid_co
   for (int c = 0; c < 3; ++c) store_seg<kTexels>(p.out.ptr + plane_off(p.out, w.b, c, w.row, w.col0), w.vec, w.valid, o[c]);
 }
 
+}  // namespace pbr
+
+#include "pbr_aux_kernels.cuh"
+
+namespace pbr {
+
 // ------------------------------------------------------------------------------------------------
 // host side of the C ABI
 // ------------------------------------------------------------------------------------------------
@@ -898,6 +904,11 @@ uint64_t pbr_sizeof(int which) {
     case 6: return sizeof(PbrBlendDesc);
     case 7: return sizeof(PbrColorDesc);
     case 8: return sizeof(PbrNormalDesc);
+    case 9: return sizeof(PbrIngestDesc);
+    case 10: return sizeof(PbrIndexMap);
+    case 11: return sizeof(PbrIndexDesc);
+    case 12: return sizeof(PbrAdamMap);
+    case 13: return sizeof(PbrAdamDesc);
     default: return 0;
   }
 }
@@ -1024,6 +1035,70 @@ int pbr_normal_ingest(const PbrNormalDesc* d, pbr_stream_t stream) {
   dim3 grid, block;
   launch_shape(k.B, k.H, k.W, grid, block);
   normal_ingest_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);
+  return launch_result();
+}
+
+int pbr_ingest_image(const PbrIngestDesc* d, pbr_stream_t stream) {
+  if (!d) return PBR_E_NULL;
+  if (int rc = check_dims(d->B, d->H, d->W)) return rc;
+  if (d->bits != 8 && d->bits != 16) return PBR_E_ENUM;
+  if (d->mode < PBR_INGEST_PLAIN || d->mode > PBR_INGEST_NORMAL2) return PBR_E_ENUM;
+  if (d->src_channels < 1 || d->src_channels > 4) return PBR_E_CHANNELS;
+  const int need = d->mode == PBR_INGEST_NORMAL3 ? 3 : (d->mode == PBR_INGEST_NORMAL2 ? 2 : d->channels);
+  if (need < 1 || need > d->src_channels) return PBR_E_CHANNELS;
+  if (!d->src || !d->out.ptr) return PBR_E_NULL;
+  IngestKParams k{};
+  k.d = *d;
+  k.vec_ok = plane_vec_ok(d->out);
+  dim3 grid, block;
+  launch_shape(d->B, d->H, d->W, grid, block);
+  ingest_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);
+  return launch_result();
+}
+
+int pbr_index_transform(const PbrIndexDesc* d, pbr_stream_t stream) {
+  if (!d) return PBR_E_NULL;
+  if (int rc = check_dims(d->B, d->H_out, d->W_out)) return rc;
+  if (d->H_in < 1 || d->W_in < 1) return PBR_E_SHAPE;
+  if ((d->step_y != 1 && d->step_y != -1) || (d->step_x != 1 && d->step_x != -1)) return PBR_E_ENUM;
+  if (d->n_maps < 0) return PBR_E_SHAPE;
+  if (d->n_maps > PBR_MAX_INDEX_MAPS) return PBR_E_TOO_MANY;
+  IndexKParams k{};
+  k.d = *d;
+  bool vec = true;
+  for (int m = 0; m < d->n_maps; ++m) {
+    const PbrIndexMap& im = d->maps[m];
+    if (!im.in.ptr || !im.out.ptr) return PBR_E_NULL;
+    if (im.channels < 1 || im.channels > 4) return PBR_E_CHANNELS;
+    vec = vec && plane_vec_ok(im.out);
+  }
+  k.vec_ok = vec;
+  dim3 grid, block;
+  launch_shape(d->B, d->H_out, d->W_out, grid, block);
+  index_transform_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);
+  return launch_result();
+}
+
+int pbr_adam_step(const PbrAdamDesc* d, pbr_stream_t stream) {
+  if (!d) return PBR_E_NULL;
+  if (int rc = check_dims(d->B, d->H, d->W)) return rc;
+  if (d->n_maps < 0) return PBR_E_SHAPE;
+  if (d->n_maps > PBR_MAX_ADAM_MAPS) return PBR_E_TOO_MANY;
+  AdamKParams k{};
+  k.d = *d;
+  bool vec = true;
+  for (int m = 0; m < d->n_maps; ++m) {
+    const PbrAdamMap& am = d->maps[m];
+    if (!am.param.ptr || !am.grad.ptr || !am.exp_avg.ptr || !am.exp_avg_sq.ptr) return PBR_E_NULL;
+    if (am.channels < 1 || am.channels > 4) return PBR_E_CHANNELS;
+    if (am.project < PBR_PROJECT_NONE || am.project > PBR_PROJECT_NORMALIZE) return PBR_E_ENUM;
+    if (am.project == PBR_PROJECT_NORMALIZE && am.channels != 3) return PBR_E_CHANNELS;
+    vec = vec && plane_vec_ok(am.param) && plane_vec_ok(am.grad) && plane_vec_ok(am.exp_avg) && plane_vec_ok(am.exp_avg_sq);
+  }
+  k.vec_ok = vec;
+  dim3 grid, block;
+  launch_shape(d->B, d->H, d->W, grid, block);
+  adam_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);
   return launch_result();
 }
 

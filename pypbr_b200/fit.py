@@ -117,6 +117,95 @@ def allreduce_loss_and_shared(buf: torch.Tensor, group=None) -> torch.Tensor:
     return buf
 
 
+# projection that keeps a fitted map valid after every optimiser step
+DEFAULT_PROJECTION = {
+    "albedo": ("clamp", 0.0, 1.0), "roughness": ("clamp", 0.0, 1.0), "metallic": ("clamp", 0.0, 1.0),
+    "specular": ("clamp", 0.0, 1.0), "height": ("clamp", 0.0, 1.0), "normal": ("normalize", 0.0, 0.0),
+}
+
+
+class FusedAdam:
+    """
+    Adam on every parameter map of a (batched) material in ONE kernel launch per step (pbr_adam_step), fused with
+    the projection onto the valid range: clamp to [0, 1] for albedo / roughness / metallic / specular, renormalise
+    for the normal map.  The update rule is torch.optim.Adam's (no weight decay, no amsgrad); the reference has no
+    optimiser code (docs/source/tutorials/06_advanced.rst:136-137 leaves it to the reader).
+
+    params: dict name -> CUDA float32 tensor (C,H,W) or (B,C,H,W), updated in place.
+    project: dict name -> ("clamp", lo, hi) | ("normalize",) | None; defaults to DEFAULT_PROJECTION by map name.
+    """
+
+    def __init__(self, params: Dict[str, torch.Tensor], lr: float = 1e-2, betas=(0.9, 0.999), eps: float = 1e-8,
+                 project: Optional[Dict[str, Optional[tuple]]] = None):
+        if not params:
+            raise ValueError("FusedAdam needs at least one parameter map")
+        if len(params) > _cabi.PBR_MAX_ADAM_MAPS:
+            raise ValueError(f"at most {_cabi.PBR_MAX_ADAM_MAPS} maps per optimiser")
+        self.params = {}
+        shape = None
+        for name, t in params.items():
+            _cabi.require_cuda(t, name)
+            if t.dim() not in (3, 4) or not t.is_contiguous():
+                raise ValueError(f"{name}: parameter maps must be contiguous (C,H,W) or (B,C,H,W) tensors")
+            key = (t.shape[0] if t.dim() == 4 else 1, t.shape[-2], t.shape[-1])
+            if shape is None:
+                shape = key
+            elif key != shape:
+                raise ValueError("all parameter maps must share batch and spatial size")
+            self.params[name] = t
+        self.B, self.H, self.W = shape
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.step_count = 0
+        self.state = {n: (torch.zeros_like(t), torch.zeros_like(t)) for n, t in self.params.items()}
+        proj = dict(DEFAULT_PROJECTION)
+        if project is not None:
+            proj.update(project)
+        self.project = {n: proj.get(n) for n in self.params}
+
+    def step(self, grads: Dict[str, torch.Tensor], grad_scale: float = 1.0) -> None:
+        """One Adam step with gradient `grads[name] * grad_scale` for every map (grads are not modified)."""
+        lib = _cabi.load()
+        self.step_count += 1
+        b1, b2 = self.betas
+        d = _cabi.PbrAdamDesc()
+        d.B, d.H, d.W, d.n_maps = self.B, self.H, self.W, len(self.params)
+        d.step_size = self.lr / (1.0 - b1 ** self.step_count)
+        d.one_minus_beta1, d.beta2, d.one_minus_beta2 = 1.0 - b1, b2, 1.0 - b2
+        d.bias2_sqrt = (1.0 - b2 ** self.step_count) ** 0.5
+        d.eps, d.grad_scale = self.eps, float(grad_scale)
+        device = None
+        for i, (name, t) in enumerate(self.params.items()):
+            g = grads[name]
+            _cabi.require_cuda(g, f"grad of {name}")
+            if g.shape != t.shape or not g.is_contiguous():
+                raise ValueError(f"grad of {name} must be a contiguous tensor of shape {tuple(t.shape)}")
+            m, v = self.state[name]
+            pr = self.project[name]
+            kind = _cabi.PROJECT_NONE if pr is None else (_cabi.PROJECT_CLAMP if pr[0] == "clamp" else _cabi.PROJECT_NORMALIZE)
+            lo, hi = (float(pr[1]), float(pr[2])) if kind == _cabi.PROJECT_CLAMP else (0.0, 0.0)
+            d.maps[i] = _cabi.PbrAdamMap(_cabi.plane(t), _cabi.plane(g), _cabi.plane(m), _cabi.plane(v), t.shape[-3], kind, lo, hi)
+            device = t.device
+        with torch.cuda.device(device):
+            _cabi.check(lib.pbr_adam_step(_cabi.byref(d), _cabi.stream_ptr(device)), "pbr_adam_step")
+
+
+def fit_step(material: MaterialBase, optimizer: FusedAdam, target: torch.Tensor, view_dir, lights, intensity,
+             light_type: str = "point", light_size: Optional[float] = None, multi_light: str = "per_light",
+             scratch: Optional[Dict[str, torch.Tensor]] = None, global_numel: Optional[int] = None) -> torch.Tensor:
+    """
+    One step of the sharded inverse-rendering fit on this rank's materials: fused render + MSE + backward
+    (pbr_ct_loss_fwd_bwd), ONE all-reduce of the loss buffer, fused Adam + projection (pbr_adam_step).
+    `global_numel`: element count of the target over ALL ranks (the MSE denominator); default: this rank's.
+    Returns the all-reduced buffer [sum of squared errors, ...] (device tensor; multiply [0] by 1/global_numel).
+    """
+    numel = global_numel if global_numel is not None else target.numel()
+    buf, grads = fused_loss_step(material, target, view_dir, lights, intensity, light_type, light_size,
+                                 multi_light=multi_light, loss_scale=1.0 / numel, out=scratch)
+    allreduce_loss_and_shared(buf)
+    optimizer.step({k: grads[k] for k in optimizer.params})
+    return buf
+
+
 class RenderingLoss(nn.Module):
     """
     The tutorial's RenderingLoss (06_advanced.rst:73-107) with the predicted render, the MSE and the

@@ -120,6 +120,13 @@ class MaterialBase:
     def _process_map(self, name, value):
         if value is None:
             return None
+        if Image is not None and isinstance(value, Image.Image) and torch.device(self.device).type == "cuda":
+            # 8/16-bit image straight to the device: /255 (/65535) and the normal remap fused in one kernel
+            from ._ingest import ingest_pil
+
+            fused = ingest_pil(value, self.device, name == "normal")
+            if fused is not None:
+                return fused
         tensor = self._to_tensor(value)
         return self._process_normal_map(tensor) if name == "normal" else tensor
 
@@ -297,10 +304,15 @@ class MaterialBase:
         return self._each(lambda _n, t: TF.crop(t, top, left, height, width))
 
     def tile(self, num_tiles: int):
+        """Repeat every map num_tiles x num_tiles (base.py:521-537: tensor.repeat)."""
+        if self._all_cuda():
+            return self._index_transform(lambda H, W: (H * num_tiles, W * num_tiles, 0, 1, 0, 1, True))
         return self._each(lambda _n, t: t.repeat(*([1] * (t.dim() - 2)), num_tiles, num_tiles))
 
     def flip_horizontal(self):
         """Mirror along W; the normal's X component changes sign (base.py:605-621)."""
+        if self._all_cuda():
+            return self._index_transform(lambda H, W: (H, W, 0, 1, W - 1, -1, False), negate={"normal": 0b001})
 
         def f(name, t):
             out = t.flip(-1)
@@ -313,6 +325,8 @@ class MaterialBase:
 
     def flip_vertical(self):
         """Mirror along H; the normal's Y component changes sign (base.py:623-639)."""
+        if self._all_cuda():
+            return self._index_transform(lambda H, W: (H, W, H - 1, -1, 0, 1, False), negate={"normal": 0b010})
 
         def f(name, t):
             out = t.flip(-2)
@@ -324,7 +338,52 @@ class MaterialBase:
         return self._each(f)
 
     def roll(self, shift: Tuple[int, int]):
+        """torch.roll(map, shift, dims=(H, W)) on every map (base.py:641-655)."""
+        if self._all_cuda():
+            return self._index_transform(lambda H, W: (H, W, (-int(shift[0])) % H, 1, (-int(shift[1])) % W, 1, True))
         return self._each(lambda _n, t: torch.roll(t, shift, dims=(-2, -1)))
+
+    # -- CUDA path of the index transforms: every map of the material in ONE gather kernel (pbr_index_transform)
+    def _all_cuda(self) -> bool:
+        ts = [t for t in self._maps.values() if t is not None]
+        return bool(ts) and all(t.is_cuda and t.dtype == torch.float32 for t in ts)
+
+    def _index_transform(self, geometry, negate: Optional[Dict[str, int]] = None):
+        """
+        geometry(H_in, W_in) -> (H_out, W_out, origin_y, step_y, origin_x, step_x, wrap).  Maps that share
+        (batch, H, W) travel in one launch; results are bit-identical to the torch calls of the reference
+        (pure data movement; the sign flip of a normal component is exact).
+        """
+        lib = _cabi.load()
+        negate = negate or {}
+        groups: Dict[tuple, list] = {}
+        for name, t in self._maps.items():
+            if t is None:
+                continue
+            if t.shape[-3] > 4:
+                raise ValueError(f"map '{name}' has {t.shape[-3]} channels; at most 4 are supported per map")
+            key = (t.shape[0] if t.dim() == 4 else 1, t.dim(), t.shape[-2], t.shape[-1], t.device)
+            groups.setdefault(key, []).append(name)
+        for (B, _dim, H, W, device), names in groups.items():
+            H_out, W_out, oy, sy, ox, sx, wrap = geometry(H, W)
+            for start in range(0, len(names), _cabi.PBR_MAX_INDEX_MAPS):
+                part = names[start : start + _cabi.PBR_MAX_INDEX_MAPS]
+                d = _cabi.PbrIndexDesc()
+                d.B, d.H_in, d.W_in, d.H_out, d.W_out = B, H, W, H_out, W_out
+                d.origin_y, d.step_y, d.origin_x, d.step_x, d.wrap = oy, sy, ox, sx, int(wrap)
+                d.n_maps = len(part)
+                keep, outs = [], {}
+                for i, name in enumerate(part):
+                    src = _cabi.rowmajor(self._maps[name].detach())
+                    out = torch.empty(*src.shape[:-2], H_out, W_out, dtype=torch.float32, device=device)
+                    d.maps[i] = _cabi.PbrIndexMap(_cabi.plane(src), _cabi.plane(out), src.shape[-3], int(negate.get(name, 0)))
+                    keep.append(src)
+                    outs[name] = out
+                with torch.cuda.device(device):
+                    _cabi.check(lib.pbr_index_transform(_cabi.byref(d), _cabi.stream_ptr(device)), "pbr_index_transform")
+                for name, out in outs.items():
+                    self._maps[name] = out
+        return self
 
     def apply_transform(self, transform):
         return self._each(lambda _n, t: transform(t))

@@ -439,3 +439,149 @@ def test_streamed_kernels_equal_generic_kernels(light_type, wf, normal):
     assert torch.allclose(a[3], b[3], rtol=1e-4, atol=1e-6)
     for k in a[4]:
         assert close(a[4][k], b[4][k], 1e-5), k
+
+
+# ---------------------------------------------------------------------------------------------- SURVEY.md §8f rows
+def test_index_transforms_are_bit_exact():
+    """flip / roll / tile of every map in one gather kernel == the reference's torch calls (torch.equal), incl. the
+    sign flip of the normal's x / y, ragged sizes, batched maps and maps of different sizes in one material."""
+    from oracle import pbr_oracle as O
+    from pypbr_b200.materials import BasecolorMetallicMaterial
+
+    g = torch.Generator().manual_seed(11)
+    for (H, W) in ((33, 47), (64, 128), (5, 3)):
+        maps = dict(albedo=torch.rand(3, H, W, generator=g), normal=torch.randn(3, H, W, generator=g),
+                    roughness=torch.rand(1, H, W, generator=g), metallic=torch.rand(1, H, W, generator=g),
+                    height=torch.rand(1, H // 2 + 1, W // 2 + 2, generator=g))
+
+        def fresh():
+            m = BasecolorMetallicMaterial(device=DEV)
+            for k, v in maps.items():
+                m._maps[k] = v.to(DEV)
+            return m
+
+        for name, ours, ref in (
+            ("flip_h", lambda m: m.flip_horizontal(), O.flip_horizontal(maps)),
+            ("flip_v", lambda m: m.flip_vertical(), O.flip_vertical(maps)),
+            ("roll", lambda m: m.roll((7, -5)), O.roll(maps, (7, -5))),
+            ("roll_big", lambda m: m.roll((-2 * H - 1, 3 * W + 2)), O.roll(maps, (-2 * H - 1, 3 * W + 2))),
+            ("tile", lambda m: m.tile(3), O.tile(maps, 3)),
+        ):
+            l0 = _cabi_launches()
+            got = ours(fresh())
+            assert _cabi_launches() > l0, "index transform did not go through the native library"
+            for k in maps:
+                assert torch.equal(got._maps[k].cpu(), ref[k]), (name, k, H, W)
+    # batched maps: a batch is B independent materials
+    B, H, W = 3, 18, 20
+    bm = dict(albedo=torch.rand(B, 3, H, W, generator=g), normal=torch.randn(B, 3, H, W, generator=g))
+    m = BasecolorMetallicMaterial(device=DEV)
+    for k, v in bm.items():
+        m._maps[k] = v.to(DEV)
+    m.flip_horizontal()
+    for b in range(B):
+        ref = O.flip_horizontal({k: v[b] for k, v in bm.items()})
+        for k in bm:
+            assert torch.equal(m._maps[k][b].cpu(), ref[k])
+
+
+def _cabi_launches():
+    from pypbr_b200 import _cabi
+
+    return _cabi.launch_count()
+
+
+def test_image_ingestion_is_bit_exact():
+    """uint8 / uint16 images straight to the device: /255, /65535 and the normal remap fused == the reference's
+    TF.to_tensor + _process_normal_map (torch.equal); also through the material constructor with PIL images."""
+    from PIL import Image
+
+    from oracle import pbr_oracle as O
+    from pypbr_b200.materials import BasecolorMetallicMaterial
+    from pypbr_b200.materials._ingest import NORMAL2, NORMAL3, PLAIN, ingest_uint
+
+    rng = np.random.default_rng(5)
+    for (H, W) in ((40, 64), (17, 23)):
+        rgb = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        rgb[0, :8, 0] = np.arange(8) * 36   # make sure 0 and 252.. are present
+        gray = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        h16 = rng.integers(0, 65536, (H, W), dtype=np.uint16)
+        assert torch.equal(ingest_uint(torch.from_numpy(rgb), DEV, PLAIN).cpu(), O.ingest_image(rgb))
+        assert torch.equal(ingest_uint(torch.from_numpy(gray), DEV, PLAIN).cpu(), O.ingest_image(gray))
+        assert torch.equal(ingest_uint(torch.from_numpy(h16.view(np.int16)), DEV, PLAIN).cpu(), O.ingest_image(h16))
+        assert torch.equal(ingest_uint(torch.from_numpy(rgb), DEV, NORMAL3).cpu(), O.ingest_image(rgb, is_normal=True))
+        two = O.process_normal_map(O.ingest_image(rgb)[:2])
+        # 2-channel maps: z = sqrt(clamp(1 - x^2 - y^2)) then normalise - within an ulp of the CPU's sqrt / vector norm
+        assert np.allclose(ingest_uint(torch.from_numpy(rgb), DEV, NORMAL2).cpu().numpy(), two.numpy(), rtol=3e-7, atol=1e-8)
+        # every byte value
+        ramp = np.arange(256, dtype=np.uint8).reshape(1, 256)
+        assert torch.equal(ingest_uint(torch.from_numpy(ramp), DEV, PLAIN).cpu(), O.ingest_image(ramp))
+        # batched (B, H, W, C)
+        bat = rng.integers(0, 256, (3, H, W, 3), dtype=np.uint8)
+        got = ingest_uint(torch.from_numpy(bat), DEV, PLAIN).cpu()
+        for b in range(3):
+            assert torch.equal(got[b], O.ingest_image(bat[b]))
+        # through the constructor, PIL in -> CUDA maps out
+        l0 = _cabi_launches()
+        mat = BasecolorMetallicMaterial(albedo=Image.fromarray(rgb), normal=Image.fromarray(rgb), roughness=Image.fromarray(gray),
+                                        metallic=Image.fromarray(gray), device=DEV)
+        assert _cabi_launches() >= l0 + 4
+        assert mat.albedo.is_cuda and torch.equal(mat.albedo.cpu(), O.ingest_image(rgb))
+        assert torch.equal(mat.normal.cpu(), O.ingest_image(rgb, is_normal=True))
+        assert torch.equal(mat.roughness.cpu(), O.ingest_image(gray))
+
+
+def test_fused_adam_matches_torch_adam_and_fit_converges():
+    """pbr_adam_step == torch.optim.Adam + projection over several steps (rel 1e-5; the moment updates are the same
+    formulas, the compiler may contract multiply-adds), then a short inverse-rendering fit must reduce the loss."""
+    from oracle import pbr_oracle as O
+    from pypbr_b200.fit import FusedAdam, fit_step
+    from pypbr_b200.materials import BasecolorMetallicMaterial
+    from pypbr_b200.models import CookTorranceBRDF
+
+    g = torch.Generator().manual_seed(21)
+    B, H, W = 2, 19, 36
+    params = dict(albedo=torch.rand(B, 3, H, W, generator=g), roughness=torch.rand(B, 1, H, W, generator=g),
+                  metallic=torch.rand(B, 1, H, W, generator=g),
+                  normal=torch.nn.functional.normalize(torch.randn(B, 3, H, W, generator=g) * 0.3 + torch.tensor([0, 0, 1.0]).view(1, 3, 1, 1), dim=1))
+    steps = [{k: torch.randn(v.shape, generator=g) * (10.0 ** (i - 2)) for k, v in params.items()} for i in range(5)]
+    ref = O.adam_fit_steps(params, steps, lr=0.05)
+    dev_params = {k: v.clone().to(DEV) for k, v in params.items()}
+    opt = FusedAdam(dev_params, lr=0.05)
+    for gr in steps:
+        opt.step({k: v.to(DEV) for k, v in gr.items()})
+    for k in params:
+        a, b = dev_params[k].cpu(), ref[k]
+        assert bool(((a - b).abs() <= 1e-5 * b.abs() + 1e-6).all()), (k, float((a - b).abs().max()))
+    assert float(dev_params["albedo"].min()) >= 0.0 and float(dev_params["albedo"].max()) <= 1.0
+    nrm = dev_params["normal"].norm(dim=1)
+    assert torch.allclose(nrm, torch.ones_like(nrm), atol=1e-6)
+    # grad_scale is applied to the gradient
+    p1 = {k: v.clone().to(DEV) for k, v in params.items()}
+    p2 = {k: v.clone().to(DEV) for k, v in params.items()}
+    FusedAdam(p1, lr=0.01).step({k: (v * 4).to(DEV) for k, v in steps[2].items()})
+    FusedAdam(p2, lr=0.01).step({k: v.to(DEV) for k, v in steps[2].items()}, grad_scale=4.0)
+    for k in p1:
+        assert torch.allclose(p1[k], p2[k], rtol=1e-6, atol=1e-7)
+
+    # a short fit: render a ground-truth batch under 3 lights, start from a perturbed copy, the loss must fall
+    maps, lights, inten, g2 = _random_case(41, 2, 32, 48, 3)
+    view = torch.tensor([0.0, 0.0, 1.0])
+    gt, _ = _material(maps, dict(light_type="point"))
+    with torch.no_grad():
+        target = CookTorranceBRDF("point", multi_light="per_light")(gt, view, lights, inten, 1.0)
+    start = {k: v.clone() for k, v in maps.items()}
+    start["albedo"] = (start["albedo"] * 0.6 + 0.2)
+    start["roughness"] = (start["roughness"] * 0.5 + 0.3)
+    pred = BasecolorMetallicMaterial(albedo_is_srgb=True, device=DEV)
+    leaves = {}
+    for k, v in start.items():
+        leaves[k] = v.contiguous().to(DEV)
+        pred._maps[k] = leaves[k]
+    opt = FusedAdam(leaves, lr=0.02)
+    losses = []
+    scratch = {}
+    for _ in range(40):
+        buf = fit_step(pred, opt, target, view, lights, inten, "point", 1.0, scratch=scratch)
+        losses.append(float(buf[0]) / target.numel())
+    assert losses[-1] < 0.25 * losses[0], losses[::8]
