@@ -2,7 +2,7 @@
 """
 bench.py — CookTorrance forward+backward throughput (BASELINE.json metric), one JSON line on stdout.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c5]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c5|aux]
 
 Workload (N=1): BASELINE.json configs[1] — batch 64 materials 1024x1024, CookTorrance forward+backward,
 1 point light, fp32, metallic workflow, sRGB albedo in / sRGB colour out.  A step = one forward pass
@@ -44,7 +44,8 @@ CONFIGS = {
     "c3": dict(B=16, H=2048, W=2048, L=16, per_light=False,
                workload="batch 16 materials 2048x2048, 16 point lights, forward+backward shading"),
     "c5": dict(B=512, H=512, W=512, L=8, per_light=True,
-               workload="SVBRDF fit step, 512 materials 512x512 per GPU, 8 lights, fused loss forward+backward"),
+               workload="SVBRDF inverse-rendering fit step, 512 materials 512x512 per GPU, 8 lights: fused render+MSE+backward, "
+                        "loss all-reduce, fused Adam+projection"),
 }
 C4 = dict(H=4096, W=4096,
           workload="4096x4096 metallic->diffuse-specular conversion + mask/height blend_materials pipeline")
@@ -220,7 +221,7 @@ def run_ours(args, cfg):
     import torch.distributed as dist
 
     from pypbr_b200 import _cabi
-    from pypbr_b200.fit import allreduce_loss_and_shared, fused_loss_step
+    from pypbr_b200.fit import FusedAdam, allreduce_loss_and_shared, fit_step, fused_loss_step
     from pypbr_b200.materials import BasecolorMetallicMaterial
     from pypbr_b200.models import CookTorranceBRDF
 
@@ -256,6 +257,10 @@ def run_ours(args, cfg):
         target = torch.rand(out_shape, generator=g, device=dev)
         bufs = {}
         grad_out = None
+        for v in leaves:
+            v.requires_grad_(False)
+        adam = FusedAdam({k: mat._maps[k] for k in ("albedo", "normal", "roughness", "metallic")}, lr=1e-3)
+        adam_ms = []
     else:
         grad_out = torch.rand(out_shape, generator=g, device=dev)
 
@@ -264,13 +269,18 @@ def run_ours(args, cfg):
 
     def step(record=False):
         if fused_fit:
-            e0, e1 = ev(), ev()
+            # one full step of the sharded fit: fused render + MSE + backward, ONE all-reduce, fused Adam + projection
+            e0, e1, e2 = ev(), ev(), ev()
             e0.record()
-            buf, _ = fused_loss_step(mat, target, view, lights, inten, "point", 1.0, multi_light="per_light", out=bufs)
-            allreduce_loss_and_shared(buf)
+            buf, grads = fused_loss_step(mat, target, view, lights, inten, "point", 1.0, multi_light="per_light",
+                                         loss_scale=1.0 / (target.numel() * world), out=bufs)
             e1.record()
+            allreduce_loss_and_shared(buf)
+            adam.step({k: grads[k] for k in adam.params})
+            e2.record()
             if record:
                 bwd_ms.append((e0, e1))
+                adam_ms.append((e1, e2))
             return
         e0, e1, e2 = ev(), ev(), ev()
         e0.record()
@@ -325,6 +335,12 @@ def run_ours(args, cfg):
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (tr or {}).get("bytes"), "traffic_source": (tr or {}).get("source"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": kbytes, "kernel_ms": bwd_avg}
+    if fused_fit:
+        a_avg = sum(a.elapsed_time(b) for a, b in adam_ms) / len(adam_ms)
+        ab = texels * 8 * 28   # 8 parameter planes: read p, g, m, v and write p, m, v
+        roofline["adam"] = {"kernel": "adam_kernel (+ the loss all-reduce when n_gpus > 1)", "kernel_ms": a_avg,
+                            "algorithmic_bytes_per_launch": ab, "achieved": ab / (a_avg * 1e-3) / 1e9,
+                            "frac": ab / (a_avg * 1e-3) / 1e9 / peak}
     if fwd_avg is not None:
         fb = texels * (FWD_BYTES if not per_light else 32 + 12 * L)
         roofline["forward"] = {"kernel": "ct_forward_kernel", "achieved": fb / (fwd_avg * 1e-3) / 1e9, "kernel_ms": fwd_avg,
@@ -368,8 +384,43 @@ def run_ours(args, cfg):
             dt = float(t.item())
         e2e = {"value": texel_lights_per_step * n_e2e / dt / 1e9, "unit": "Gtexel-lights/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4, "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
-               "path": "pinned host maps -> .to(cuda) -> pypbr_b200.fit.fused_loss_step (pbr_ct_loss_fwd_bwd) -> loss.item()"}
+               "path": "pinned host float32 maps -> .to(cuda) -> pypbr_b200.fit.fused_loss_step (pbr_ct_loss_fwd_bwd) -> loss.item()",
+               "bound": f"PCIe: {h2d / (dt / n_e2e) / 1e9:.1f} GB/s host->device"}
         del host, host_mat
+        # the same step fed with 8-bit textures (what a dataset on disk holds): 8 bytes per texel cross PCIe instead of
+        # 32 and pbr_ingest_image expands them on the device
+        from pypbr_b200.materials._ingest import NORMAL3, PLAIN, ingest_uint
+
+        g8 = torch.Generator().manual_seed(77 + rank)
+        host8 = {k: torch.randint(0, 256, (B, H, W, c), dtype=torch.uint8, generator=g8).pin_memory()
+                 for k, c in (("albedo", 3), ("normal", 3), ("roughness", 1), ("metallic", 1))}
+        h2d8 = sum(v.numel() for v in host8.values())
+
+        def e2e8_step():
+            dmat = BasecolorMetallicMaterial(albedo_is_srgb=True, device=dev)
+            for k, v in host8.items():
+                dmat._maps[k] = ingest_uint(v, dev, NORMAL3 if k == "normal" else PLAIN)
+            buf, _ = fused_loss_step(dmat, tgt, view, lights, inten, "point", 1.0,
+                                     multi_light="per_light" if per_light else "accumulate", out=bufs2)
+            return float(buf[0].item())
+
+        for _ in range(2):
+            e2e8_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e8_step()
+        torch.cuda.synchronize()
+        dt8 = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt8], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt8 = float(t.item())
+        e2e["uint8_textures"] = {"value": texel_lights_per_step * n_e2e / dt8 / 1e9, "unit": "Gtexel-lights/s",
+                                 "h2d_bytes_per_step": h2d8, "d2h_bytes_per_step": 4, "ms_per_step": dt8 / n_e2e * 1e3,
+                                 "path": "pinned host uint8 (B,H,W,C) images -> .to(cuda) -> pbr_ingest_image x4 -> "
+                                         "pbr_ct_loss_fwd_bwd -> loss.item()"}
+        del host8
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -384,7 +435,7 @@ def run_ours(args, cfg):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["workload"], "per_gpu_batch": B, "H": H, "W": W, "lights": L,
-                       "mode": "per_light fused loss" if fused_fit else "accumulate", "parallelism": f"batch-shard x{world}",
+                       "mode": "per_light fused loss + Adam" if fused_fit else "accumulate", "parallelism": f"batch-shard x{world}",
                        "l2": "inputs (2.1 GB per GPU) exceed the 126 MB L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk.summary(),
@@ -530,13 +581,93 @@ def run_c4(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------- aux rows
+def run_aux(args):
+    """Kernel-only timings of the rows either side of the shading path: image ingestion, index transforms, Adam."""
+    from pypbr_b200 import _cabi
+    from pypbr_b200.fit import FusedAdam
+    from pypbr_b200.materials import BasecolorMetallicMaterial
+    from pypbr_b200.materials._ingest import NORMAL3, PLAIN, ingest_uint
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    _cabi.load()
+    B, H, W = 16, 2048, 2048
+    texels = B * H * W
+    peak, peak_src = measured_peak()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    kernels = {}
+
+    def add(name, ms, nbytes):
+        ach = nbytes / (ms * 1e-3) / 1e9
+        kernels[name] = {"ms": ms, "algorithmic_bytes": nbytes, "achieved": ach, "frac": ach / peak}
+
+    l0 = _cabi.launch_count()
+    with ClockSampler(local) as clk:
+        g = torch.Generator(device=dev).manual_seed(8)
+        rgb8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=dev, generator=g)
+        add("ingest uint8 RGB -> float32 planar", timed(lambda: ingest_uint(rgb8, dev, PLAIN)), texels * (3 + 12))
+        add("ingest uint8 RGB -> unit normal", timed(lambda: ingest_uint(rgb8, dev, NORMAL3)), texels * (3 + 12))
+        del rgb8
+        maps = synth_maps(B, H, W, dev, 9)
+        mat = BasecolorMetallicMaterial(albedo_is_srgb=True, device=dev)
+
+        def reset():
+            for k, v in maps.items():
+                mat._maps[k] = v
+
+        def flip():
+            reset()
+            mat.flip_horizontal()
+
+        def rollit():
+            reset()
+            mat.roll((17, -33))
+
+        add("flip_horizontal, 4 maps (8 channels) in one gather", timed(flip), texels * 8 * 8)
+        add("roll, 4 maps (8 channels) in one gather", timed(rollit), texels * 8 * 8)
+        reset()
+        opt = FusedAdam({k: v for k, v in maps.items()}, lr=1e-3)
+        grads = {k: torch.rand_like(v) for k, v in maps.items()}
+        add("Adam + projection, 4 maps (8 channels)", timed(lambda: opt.step(grads)), texels * 8 * 28)
+    launches = _cabi.launch_count() - l0
+    dom = max(kernels.items(), key=lambda kv: kv[1]["ms"])
+    line = {
+        "metric": "GB/s of the ingestion / index-transform / optimiser kernels", "value": dom[1]["achieved"], "unit": "GB/s",
+        "n_gpus": 1, "steps": 10, "warmup": 3, "ms_per_step": dom[1]["ms"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"SURVEY 8f rows on {B} materials {H}x{W}: image ingestion, index transforms, Adam step",
+                   "l2": "every kernel streams 1-15 GB, far above the 126 MB L2; no flush needed"},
+        "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": dom[1]["achieved"], "peak": peak, "unit": "GB/s",
+                     "frac": dom[1]["frac"], "traffic": None, "peak_source": peak_src, "kernels": kernels},
+        "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clk.summary(),
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(list(CONFIGS) + ["c4"]))
+    ap.add_argument("--config", default="c2", choices=sorted(list(CONFIGS) + ["c4", "aux"]))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -544,6 +675,8 @@ def main():
         if args.impl == "reference":
             raise SystemExit("bench.py: the reference arm is defined for the shading configs (c2/c3/c5) only")
         return run_c4(args)
+    if args.config == "aux":
+        return run_aux(args)
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
         run_reference_arm(args, cfg)

@@ -17,57 +17,67 @@ namespace pbr {
 struct IngestKParams {
   PbrIngestDesc d;
   int vec_ok;
+  int src_words_ok;   // source base and strides are 4-byte aligned: a thread's 4 pixels are read as whole words
 };
 
-__device__ __forceinline__ unsigned ingest_raw(const PbrIngestDesc& d, int b, int row, int col, int c) {
-  const unsigned char* base = static_cast<const unsigned char*>(d.src) + (int64_t)b * d.src_batch_stride + (int64_t)row * d.src_row_stride;
-  if (d.bits == 8) return base[(int64_t)col * d.src_channels + c];
-  return reinterpret_cast<const unsigned short*>(base)[(int64_t)col * d.src_channels + c];
-}
-
+// CS interleaved source channels of BITS bits: the 4 pixels of a thread are 4*CS*BITS/8 contiguous bytes, i.e.
+// CS*BITS/8 32-bit words when the row is word aligned; otherwise (and at a ragged edge) element loads.
+template <int CS, int BITS>
 __global__ void __launch_bounds__(kThreads) ingest_kernel(const __grid_constant__ IngestKParams p) {
   const PbrIngestDesc& d = p.d;
   // x / 255 for every byte value, computed once per CTA with the IEEE division torch uses: exact by construction
   __shared__ float lut[256];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  if (d.bits == 8)
+  if (BITS == 8)
     for (int i = tid; i < 256; i += kThreads) lut[i] = xdiv((float)i, 255.0f);
   __syncthreads();
   const Where w = locate(d.H, d.W, p.vec_ok != 0);
   if (!w.active) return;
-  const int cin = d.mode == PBR_INGEST_NORMAL2 ? 2 : (d.mode == PBR_INGEST_NORMAL3 ? 3 : d.channels);
-  float v[3][kTexels], o[3][kTexels];
-  for (int c = 0; c < cin && c < 3; ++c)
+  constexpr int ESZ = BITS / 8;
+  constexpr int NW = CS * ESZ;   // words per 4 pixels
+  const unsigned char* row = static_cast<const unsigned char*>(d.src) + (int64_t)w.b * d.src_batch_stride + (int64_t)w.row * d.src_row_stride;
+  unsigned raw[kTexels][CS];
+  if (p.src_words_ok && w.valid == kTexels && kTexels == 4) {
+    unsigned words[NW];
+    const unsigned* wp = reinterpret_cast<const unsigned*>(row + (int64_t)w.col0 * CS * ESZ);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) words[k] = __ldcs(wp + k);
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i)
+#pragma unroll
+      for (int c = 0; c < CS; ++c) {
+        const int byte = (i * CS + c) * ESZ;
+        raw[i][c] = BITS == 8 ? (words[byte >> 2] >> ((byte & 3) * 8)) & 0xffu : (words[byte >> 2] >> ((byte & 3) * 8)) & 0xffffu;
+      }
+  } else {
 #pragma unroll
     for (int i = 0; i < kTexels; ++i) {
       const int col = w.col0 + (i < w.valid ? i : w.valid - 1);
-      const unsigned raw = ingest_raw(d, w.b, w.row, col, c);
-      v[c][i] = d.bits == 8 ? lut[raw] : xdiv((float)raw, 65535.0f);
-    }
-  if (d.mode == PBR_INGEST_PLAIN) {
-    for (int c = 0; c < d.channels; ++c) {
-      if (c >= 3) {  // 4th channel (alpha) of a plain map
 #pragma unroll
-        for (int i = 0; i < kTexels; ++i) {
-          const int col = w.col0 + (i < w.valid ? i : w.valid - 1);
-          const unsigned raw = ingest_raw(d, w.b, w.row, col, c);
-          v[0][i] = d.bits == 8 ? lut[raw] : xdiv((float)raw, 65535.0f);
-        }
-        store_seg<kTexels>(d.out.ptr + plane_off(d.out, w.b, c, w.row, w.col0), w.vec, w.valid, v[0]);
-      } else {
-        store_seg<kTexels>(d.out.ptr + plane_off(d.out, w.b, c, w.row, w.col0), w.vec, w.valid, v[c]);
-      }
+      for (int c = 0; c < CS; ++c)
+        raw[i][c] = BITS == 8 ? row[(int64_t)col * CS + c] : reinterpret_cast<const unsigned short*>(row)[(int64_t)col * CS + c];
     }
+  }
+  float v[CS][kTexels];
+#pragma unroll
+  for (int c = 0; c < CS; ++c)
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i) v[c][i] = BITS == 8 ? lut[raw[i][c]] : xdiv((float)raw[i][c], 65535.0f);
+  if (d.mode == PBR_INGEST_PLAIN) {
+#pragma unroll
+    for (int c = 0; c < CS; ++c)
+      if (c < d.channels) store_seg<kTexels>(d.out.ptr + plane_off(d.out, w.b, c, w.row, w.col0), w.vec, w.valid, v[c]);
     return;
   }
+  float o[3][kTexels];
 #pragma unroll
   for (int i = 0; i < kTexels; ++i) {
     float o3[3];
     if (d.mode == PBR_INGEST_NORMAL3) {
-      const float v3[3] = {v[0][i], v[1][i], v[2][i]};
+      const float v3[3] = {v[0][i], v[CS > 1 ? 1 : 0][i], v[CS > 2 ? 2 : 0][i]};
       ingest_normal3(v3, o3);
     } else {
-      const float v2[2] = {v[0][i], v[1][i]};
+      const float v2[2] = {v[0][i], v[CS > 1 ? 1 : 0][i]};
       ingest_normal2(v2, o3);
     }
 #pragma unroll

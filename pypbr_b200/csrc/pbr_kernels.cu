@@ -507,6 +507,21 @@ __device__ __forceinline__ float warp_min(float v) {
   return v;
 }
 
+// CTA-wide minimum -> ONE atomic per CTA (a per-warp atomic on a single address serialises ~10^5 operations per
+// launch at 4096^2).  Every thread of the CTA must call it.
+__device__ __forceinline__ void cta_min_atomic(float v, float* dst) {
+  __shared__ float s_min[kThreads / 32];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  v = warp_min(v);
+  if ((tid & 31) == 0) s_min[tid >> 5] = v;
+  __syncthreads();
+  if (tid == 0) {
+    float m = s_min[0];
+    for (int i = 1; i < kThreads / 32; ++i) m = fminf(m, s_min[i]);
+    if (m != INFINITY) atomic_min_float(dst, m);
+  }
+}
+
 struct BlendKParams {
   PbrBlendDesc d;
   int vec_ok;
@@ -577,11 +592,7 @@ __global__ void __launch_bounds__(kThreads) blend_kernel(const __grid_constant__
       }
     }
   }
-  if (d.normal_min) {
-    if (!w.active) nmin = INFINITY;
-    nmin = warp_min(nmin);
-    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && nmin != INFINITY) atomic_min_float(d.normal_min, nmin);
-  }
+  if (d.normal_min) cta_min_atomic(w.active ? nmin : INFINITY, d.normal_min);
 }
 
 struct ColorKParams {
@@ -617,9 +628,7 @@ __global__ void __launch_bounds__(kThreads) normal_min_kernel(const __grid_const
     for (int i = 0; i < kTexels; ++i)
       if (i < w.valid) mn = fminf(mn, v[i]);
   }
-  if (!w.active) mn = INFINITY;
-  mn = warp_min(mn);
-  if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && mn != INFINITY) atomic_min_float(p.result, mn);
+  cta_min_atomic(w.active ? mn : INFINITY, p.result);
 }
 
 __global__ void __launch_bounds__(kThreads) normal_ingest_kernel(const __grid_constant__ NormalKParams p) {
@@ -1050,9 +1059,20 @@ int pbr_ingest_image(const PbrIngestDesc* d, pbr_stream_t stream) {
   IngestKParams k{};
   k.d = *d;
   k.vec_ok = plane_vec_ok(d->out);
+  k.src_words_ok = (reinterpret_cast<uintptr_t>(d->src) % 4 == 0) && (d->src_row_stride % 4 == 0) && (d->src_batch_stride % 4 == 0);
   dim3 grid, block;
   launch_shape(d->B, d->H, d->W, grid, block);
-  ingest_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d->src_channels * 2 + (d->bits == 16)) {
+    case 2: ingest_kernel<1, 8><<<grid, block, 0, st>>>(k); break;
+    case 3: ingest_kernel<1, 16><<<grid, block, 0, st>>>(k); break;
+    case 4: ingest_kernel<2, 8><<<grid, block, 0, st>>>(k); break;
+    case 5: ingest_kernel<2, 16><<<grid, block, 0, st>>>(k); break;
+    case 6: ingest_kernel<3, 8><<<grid, block, 0, st>>>(k); break;
+    case 7: ingest_kernel<3, 16><<<grid, block, 0, st>>>(k); break;
+    case 8: ingest_kernel<4, 8><<<grid, block, 0, st>>>(k); break;
+    default: ingest_kernel<4, 16><<<grid, block, 0, st>>>(k); break;
+  }
   return launch_result();
 }
 
