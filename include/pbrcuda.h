@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PBR_ABI_VERSION 3
+#define PBR_ABI_VERSION 4
 #define PBR_MAX_LIGHTS 64      /* lights per launch (parameters are staged in shared memory) */
 #define PBR_MAX_BLEND_MAPS 12  /* maps blended by one pbr_blend launch */
 #define PBR_MAX_INDEX_MAPS 12  /* maps moved by one pbr_index_transform launch */
@@ -233,12 +233,34 @@ typedef struct PbrAdamDesc {
   PbrAdamMap maps[PBR_MAX_ADAM_MAPS];
 } PbrAdamDesc;
 
+/*
+ * Fused fit step ("Adam ... fused into K3's epilogue"): pbr_ct_loss_fwd_bwd whose epilogue
+ * applies the Adam update + projection of pbr_adam_step to the maps IN PLACE (desc->albedo / normal / roughness /
+ * metspec are written) instead of storing the gradients: per texel the 32 B of gradients are neither written nor
+ * read back, and the optimiser's pass over parameters and moments rides along a kernel that is FP32-bound.
+ * Gradients are d(loss_scale * sum((render - target)^2))/d(map), so loss_scale must already be 1/(global numel);
+ * the loss all-reduce of a sharded fit is only needed for reporting and stays off the critical path.
+ * project != 0: clamp albedo / roughness / metallic | specular to [0,1], renormalise the normal (eps 1e-12).
+ * m_normal / v_normal are ignored when desc->normal.ptr is NULL.
+ */
+typedef struct PbrCtAdam {
+  PbrPlane m_albedo, v_albedo;        /* exp_avg, exp_avg_sq: same shapes as the maps, updated in place */
+  PbrPlane m_normal, v_normal;
+  PbrPlane m_roughness, v_roughness;
+  PbrPlane m_metspec, v_metspec;
+  float step_size, one_minus_beta1, beta2, one_minus_beta2, bias2_sqrt, eps;   /* as in PbrAdamDesc */
+  int32_t project;
+} PbrCtAdam;
+
 int pbr_abi_version(void);
 const char* pbr_strerror(int code);
 
 int pbr_ct_forward(const PbrCtDesc* desc, pbr_stream_t stream);
 int pbr_ct_backward(const PbrCtDesc* desc, const PbrCtGrads* grads, pbr_stream_t stream);
 int pbr_ct_loss_fwd_bwd(const PbrCtDesc* desc, const PbrCtLoss* loss, const PbrCtGrads* grads, pbr_stream_t stream);
+/* d_intensity: device, L*3, accumulated with atomics (caller zero-fills); may be NULL */
+int pbr_ct_fit_step(const PbrCtDesc* desc, const PbrCtLoss* loss, const PbrCtAdam* adam, float* d_intensity,
+                    pbr_stream_t stream);
 
 int pbr_convert_m2s(const PbrConvDesc* desc, pbr_stream_t stream);
 int pbr_convert_s2m(const PbrConvDesc* desc, pbr_stream_t stream);
@@ -252,7 +274,7 @@ int pbr_adam_step(const PbrAdamDesc* desc, pbr_stream_t stream);
 
 /* sizeof() of the descriptor structs as THIS library was compiled (binding self-check):
    which = 0 PbrPlane, 1 PbrCtDesc, 2 PbrCtGrads, 3 PbrCtLoss, 4 PbrConvDesc, 5 PbrBlendMap, 6 PbrBlendDesc,
-   7 PbrColorDesc, 8 PbrNormalDesc, 9 PbrIngestDesc, 10 PbrIndexMap, 11 PbrIndexDesc, 12 PbrAdamMap, 13 PbrAdamDesc;
+   7 PbrColorDesc, 8 PbrNormalDesc, 9 PbrIngestDesc, 10 PbrIndexMap, 11 PbrIndexDesc, 12 PbrAdamMap, 13 PbrAdamDesc, 14 PbrCtAdam;
    anything else returns 0. */
 uint64_t pbr_sizeof(int which);
 

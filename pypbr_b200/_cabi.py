@@ -16,7 +16,7 @@ from typing import Optional, Sequence
 
 import torch
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 PBR_MAX_LIGHTS = 64
 PBR_MAX_BLEND_MAPS = 12
 PBR_MAX_INDEX_MAPS = 12
@@ -132,15 +132,24 @@ class PbrAdamDesc(Structure):
     ]
 
 
+class PbrCtAdam(Structure):
+    _fields_ = [
+        ("m_albedo", PbrPlane), ("v_albedo", PbrPlane), ("m_normal", PbrPlane), ("v_normal", PbrPlane),
+        ("m_roughness", PbrPlane), ("v_roughness", PbrPlane), ("m_metspec", PbrPlane), ("v_metspec", PbrPlane),
+        ("step_size", c_float), ("one_minus_beta1", c_float), ("beta2", c_float), ("one_minus_beta2", c_float),
+        ("bias2_sqrt", c_float), ("eps", c_float), ("project", c_int32),
+    ]
+
+
 # order = the `which` argument of pbr_sizeof()
 STRUCTS = (PbrPlane, PbrCtDesc, PbrCtGrads, PbrCtLoss, PbrConvDesc, PbrBlendMap, PbrBlendDesc, PbrColorDesc, PbrNormalDesc,
-           PbrIngestDesc, PbrIndexMap, PbrIndexDesc, PbrAdamMap, PbrAdamDesc)
+           PbrIngestDesc, PbrIndexMap, PbrIndexDesc, PbrAdamMap, PbrAdamDesc, PbrCtAdam)
 
 _lib = None
 
 # every symbol include/pbrcuda.h declares (tests check that the built library exports all of them)
 EXPORTS = (
-    "pbr_abi_version", "pbr_strerror", "pbr_ct_forward", "pbr_ct_backward", "pbr_ct_loss_fwd_bwd",
+    "pbr_abi_version", "pbr_strerror", "pbr_ct_forward", "pbr_ct_backward", "pbr_ct_loss_fwd_bwd", "pbr_ct_fit_step",
     "pbr_convert_m2s", "pbr_convert_s2m", "pbr_blend", "pbr_color_convert", "pbr_normal_min",
     "pbr_normal_ingest", "pbr_ingest_image", "pbr_index_transform", "pbr_adam_step", "pbr_launch_count", "pbr_sizeof",
 )
@@ -171,6 +180,7 @@ def load():
     lib.pbr_ct_forward.argtypes = [POINTER(PbrCtDesc), c_void_p]
     lib.pbr_ct_backward.argtypes = [POINTER(PbrCtDesc), POINTER(PbrCtGrads), c_void_p]
     lib.pbr_ct_loss_fwd_bwd.argtypes = [POINTER(PbrCtDesc), POINTER(PbrCtLoss), POINTER(PbrCtGrads), c_void_p]
+    lib.pbr_ct_fit_step.argtypes = [POINTER(PbrCtDesc), POINTER(PbrCtLoss), POINTER(PbrCtAdam), c_void_p, c_void_p]
     lib.pbr_convert_m2s.argtypes = [POINTER(PbrConvDesc), c_void_p]
     lib.pbr_convert_s2m.argtypes = [POINTER(PbrConvDesc), c_void_p]
     lib.pbr_blend.argtypes = [POINTER(PbrBlendDesc), c_void_p]

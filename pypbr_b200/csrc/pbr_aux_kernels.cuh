@@ -148,10 +148,8 @@ struct AdamKParams {
 };
 
 __device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, const PbrAdamDesc& d) {
-  m = m + (g - m) * d.one_minus_beta1;
-  v = v * d.beta2 + d.one_minus_beta2 * g * g;
-  const float denom = xdiv(xsqrt(v), d.bias2_sqrt) + d.eps;
-  return p - d.step_size * xdiv(m, denom);
+  const AdamCoef a{d.step_size, d.one_minus_beta1, d.beta2, d.one_minus_beta2, d.bias2_sqrt, d.eps};
+  return adam_update(p, g, m, v, a);   // defined next to the fused fit epilogue in pbr_kernels.cu
 }
 
 __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ AdamKParams p) {

@@ -124,6 +124,18 @@ constexpr int kSlots = kCtTexels / kLanes;
 #define PBR_BWD_GROUP 1   // ... by the generic backward kernel (register pressure)
 #endif
 
+// torch.optim.Adam (single-tensor path): m = lerp(m, g, 1-b1); v = v*b2 + (1-b2)*g*g;
+// p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps).  Shared by adam_kernel and the fused fit epilogue.
+struct AdamCoef {
+  float step_size, one_minus_beta1, beta2, one_minus_beta2, bias2_sqrt, eps;
+};
+__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, const AdamCoef& d) {
+  m = m + (g - m) * d.one_minus_beta1;
+  v = v * d.beta2 + d.one_minus_beta2 * g * g;
+  const float denom = xdiv(xsqrt(v), d.bias2_sqrt) + d.eps;
+  return p - d.step_size * xdiv(m, denom);
+}
+
 struct CtKParams {
   int B, H, W;
   int mats_per_cta;      // materials a thread walks over (blockIdx.z selects the chunk)
@@ -140,6 +152,11 @@ struct CtKParams {
   float* d_intensity;
   float loss_scale;
   float* loss_sum;
+  // fused fit step (pbr_ct_fit_step): the epilogue applies Adam + projection to the maps in place instead of
+  // writing the gradients.  Moments in the order albedo, normal, roughness, metspec.
+  int adam_on, adam_project;
+  AdamCoef adam;
+  PbrPlane adam_m[4], adam_v[4];
   // staging sources
   Linspace lsx, lsy;
   const float* view_dev;    // non-null: parameters live in device memory
@@ -215,9 +232,16 @@ __device__ __forceinline__ void unpair_to(const V (&src)[G], int s0, float (&dst
     for (int k = 0; k < kLanes; ++k) dst[kLanes * (s0 + i) + k] = lane_get(src[i], k);
 }
 
+// dynamic shared memory of the kLightPointCached* kernels: the geometry cache, L * geom_fields * kSlots * kCtThreads V's
+extern __shared__ __align__(16) unsigned char s_dyn[];
+
 template <int kLight>
-__device__ __forceinline__ void grid_coords(const CtStage& S, const Where& w, V (&x)[kSlots], float& y,
-                                            LightGeomT<V> (&hg)[kSlots]) {
+__device__ __forceinline__ void grid_coords(const CtStage& S, const Where& w, int L, V (&x)[kSlots], float& y,
+                                            LightGeomT<V> (&hg)[kSlots], GeomCache<V>& gc) {
+  gc.base = reinterpret_cast<V*>(s_dyn) + (threadIdx.y * blockDim.x + threadIdx.x);
+  gc.stride = kCtThreads;
+  gc.fstride = kSlots * kCtThreads;
+  (void)L;
 #pragma unroll
   for (int i = 0; i < kSlots; ++i)
 #pragma unroll
@@ -230,6 +254,17 @@ __device__ __forceinline__ void grid_coords(const CtStage& S, const Where& w, V 
 #pragma unroll
     for (int i = 0; i < kSlots; ++i)
       point_light_geom(S.light[0].p[0], S.light[0].p[1], S.light[0].p[2], x[i], y, S.vx, S.vy, S.vz, hg[i]);
+  }
+  if (is_cached(kLight)) {
+    // every light's geometry once per texel pair, reused by all the materials this thread walks over
+    for (int l = 0; l < L; ++l) {
+#pragma unroll
+      for (int i = 0; i < kSlots; ++i) {
+        LightGeomT<V> g;
+        point_light_geom(S.light[l].p[0], S.light[l].p[1], S.light[l].p[2], x[i], y, S.vx, S.vy, S.vz, g);
+        geom_cache_store<geom_fields(kLight), V>(gc, l, i, g);
+      }
+    }
   }
 }
 
@@ -244,7 +279,8 @@ __global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kerne
   V x[kSlots];
   float y;
   LightGeomT<V> hg[kSlots];
-  grid_coords<kLight>(S, w, x, y, hg);
+  GeomCache<V> gc;
+  grid_coords<kLight>(S, w, p.flags.L, x, y, hg, gc);
 
   const int b0 = blockIdx.z * p.mats_per_cta;
   const int b1 = min(b0 + p.mats_per_cta, p.B);
@@ -275,7 +311,9 @@ __global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kerne
           for (int c = 0; c < 3; ++c) unpair_to<G>(v[c], s, outv[c]);
         }
       };
-      ct_forward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, emit);
+      GeomCache<V> gcs = gc;   // lane-value i of the group is lane-value s + i of the thread
+      gcs.base += s * gc.stride;
+      ct_forward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, emit, gcs);
     }
     if (!p.flags.per_light) {
 #pragma unroll
@@ -307,8 +345,16 @@ __device__ __forceinline__ float warp_sum(float v) {
 //   p.is_loss     : gsrc is the target image; grad_out = 2*loss_scale*(render - target) and the squared
 //                   error is reduced warp-shuffle -> shared -> ONE atomic per CTA.
 //   p.d_intensity : per-light intensity gradients, reduced the same way.
+// CTAs per SM the backward's register budget is sized for.  With the 6-field cache the shared memory already caps
+// the SM at 2-3 CTAs and the light loop is long: the full 255-register budget (no spills) beats a third CTA
+// (tools/tune.py, L = 8: 3.29 vs 3.80 ms; L = 16: 2.53 vs 2.99 ms).
+#ifndef PBR_BWD_CACHED_MIN_CTAS
+#define PBR_BWD_CACHED_MIN_CTAS 2
+#endif
+constexpr int bwd_min_ctas(int light_mode) { return light_mode == kLightPointCached ? PBR_BWD_CACHED_MIN_CTAS : PBR_BWD_MIN_CTAS; }
+
 template <int WF, int kLight>
-__global__ void __launch_bounds__(kCtThreads, PBR_BWD_MIN_CTAS) ct_backward_kernel(const __grid_constant__ CtKParams p) {
+__global__ void __launch_bounds__(kCtThreads, bwd_min_ctas(kLight)) ct_backward_kernel(const __grid_constant__ CtKParams p) {
   constexpr int G = PBR_BWD_GROUP;
   __shared__ CtStage S;
   __shared__ float s_int[PBR_MAX_LIGHTS * 3];
@@ -328,7 +374,8 @@ __global__ void __launch_bounds__(kCtThreads, PBR_BWD_MIN_CTAS) ct_backward_kern
   V x[kSlots];
   float y;
   LightGeomT<V> hg[kSlots];
-  grid_coords<kLight>(S, w, x, y, hg);
+  GeomCache<V> gc;
+  grid_coords<kLight>(S, w, p.flags.L, x, y, hg, gc);
 
   float loss_local = 0.0f;
   const int b0 = blockIdx.z * p.mats_per_cta;
@@ -414,12 +461,69 @@ __global__ void __launch_bounds__(kCtThreads, PBR_BWD_MIN_CTAS) ct_backward_kern
         }
       };
       V da[3][G], dn[3][G], dr[G], dm[3][G];
-      ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch);
+      GeomCache<V> gcs = gc;
+      gcs.base += s * gc.stride;
+      ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs);
 #pragma unroll
       for (int c = 0; c < 3; ++c) { unpair_to<G>(da[c], s, d_albedo[c]); unpair_to<G>(dn[c], s, d_normal[c]); unpair_to<G>(dm[c], s, d_met[c]); }
       unpair_to<G>(dr, s, d_rough);
     }
-    if (w.active) {
+    if (w.active && p.adam_on) {
+      // fused fit step: the gradients never reach HBM.  Re-read the parameters (L2 / HBM: 32 B per texel in a kernel
+      // that is FP32-pipe bound) rather than keeping 16 registers alive across the light loop.
+      constexpr int mc = WF == 0 ? 1 : 3;
+      const bool proj = p.adam_project != 0;
+      auto channel = [&](const PbrPlane& P, int q, int c, const float(&g)[kCtTexels], float(&pn)[kCtTexels]) {
+        float pv[kCtTexels], m[kCtTexels], v[kCtTexels];
+        const int64_t om = plane_off(p.adam_m[q], b, c, w.row, w.col0), ov = plane_off(p.adam_v[q], b, c, w.row, w.col0);
+        load_seg<kCtTexels>(P.ptr + plane_off(P, b, c, w.row, w.col0), w.vec, w.valid, pv);
+        load_seg<kCtTexels>(p.adam_m[q].ptr + om, w.vec, w.valid, m);
+        load_seg<kCtTexels>(p.adam_v[q].ptr + ov, w.vec, w.valid, v);
+#pragma unroll
+        for (int i = 0; i < kCtTexels; ++i) pn[i] = adam_update(pv[i], g[i], m[i], v[i], p.adam);
+        store_seg<kCtTexels>(p.adam_m[q].ptr + om, w.vec, w.valid, m);
+        store_seg<kCtTexels>(p.adam_v[q].ptr + ov, w.vec, w.valid, v);
+      };
+      auto put = [&](const PbrPlane& P, int c, float(&pn)[kCtTexels], bool clamp) {
+        if (clamp) {
+#pragma unroll
+          for (int i = 0; i < kCtTexels; ++i) pn[i] = fminf(fmaxf(pn[i], 0.0f), 1.0f);
+        }
+        store_seg<kCtTexels>(const_cast<float*>(P.ptr) + plane_off(P, b, c, w.row, w.col0), w.vec, w.valid, pn);
+      };
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float pn[kCtTexels];
+        channel(p.albedo, 0, c, d_albedo[c], pn);
+        put(p.albedo, c, pn, proj);
+      }
+      if (p.normal.ptr) {
+        float pn[3][kCtTexels];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) channel(p.normal, 1, c, d_normal[c], pn[c]);
+        if (proj) {
+#pragma unroll
+          for (int i = 0; i < kCtTexels; ++i) {
+            float o3[3];
+            normalize3(pn[0][i], pn[1][i], pn[2][i], o3);   // F.normalize(dim=channel), eps 1e-12
+            pn[0][i] = o3[0]; pn[1][i] = o3[1]; pn[2][i] = o3[2];
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) put(p.normal, c, pn[c], false);
+      }
+      {
+        float pn[kCtTexels];
+        channel(p.roughness, 2, 0, d_rough, pn);
+        put(p.roughness, 0, pn, proj);
+      }
+#pragma unroll
+      for (int c = 0; c < mc; ++c) {
+        float pn[kCtTexels];
+        channel(p.metspec, 3, c, d_met[c], pn);
+        put(p.metspec, c, pn, proj);
+      }
+    } else if (w.active) {
       if (p.d_albedo.ptr) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) store_seg<kCtTexels>(p.d_albedo.ptr + plane_off(p.d_albedo, b, c, w.row, w.col0), w.vec, w.valid, d_albedo[c]);
@@ -730,15 +834,50 @@ static int launch_result() {
 // so a thread walks over up to kHoistMats materials and computes it once.
 constexpr int kHoistMats = PBR_HOIST_MATS;
 
+// Point lights with L > 1: the geometry of every light is computed once per texel pair, parked in shared memory
+// (GeomCache, pbr_shade.cuh) and reused by every material of the walk - it is ~55 % of the forward arithmetic of a
+// texel-light.  Worth it from two materials on, and while the cache leaves room for enough CTAs per SM.
+#ifndef PBR_GC_MAX_BYTES
+#define PBR_GC_MAX_BYTES (100 * 1024)   // L <= 16 with the 6-field cache: at least 2 CTAs per SM
+#endif
+#ifndef PBR_GC_ALL_MAX_LIGHTS
+#define PBR_GC_ALL_MAX_LIGHTS 4   // up to here all 8 geometry fields are cached and the backward keeps 3 CTAs per SM
+#endif
+static size_t geom_cache_bytes(int L, int light_mode) { return (size_t)L * geom_fields(light_mode) * kSlots * kCtThreads * sizeof(V); }
+static bool geom_cache_disabled() {
+  static const bool off = [] { const char* e = getenv("PBR_DISABLE_GEOM_CACHE"); return e && e[0] && e[0] != '0'; }();
+  return off;
+}
+
 static int light_mode(const CtKParams& k) {
   if (!k.flags.point) return kLightDirectional;
-  return k.flags.L == 1 ? kLightPointHoisted : kLightPoint;
+  if (k.flags.L == 1) return kLightPointHoisted;
+  if (k.B >= 2 && !geom_cache_disabled()) {
+    if (k.flags.L <= PBR_GC_ALL_MAX_LIGHTS) return kLightPointCachedAll;
+    if (geom_cache_bytes(k.flags.L, kLightPointCached) <= (size_t)PBR_GC_MAX_BYTES) return kLightPointCached;
+  }
+  return kLightPoint;
 }
 
 static void ct_launch_shape(CtKParams& k, dim3& grid, dim3& block) {
   launch_shape(k.B, k.H, k.W, grid, block, kCtThreads, kCtTexels);
-  k.mats_per_cta = (light_mode(k) == kLightPointHoisted) ? (k.B < kHoistMats ? k.B : kHoistMats) : 1;
+  const int lm = light_mode(k);
+  k.mats_per_cta = (lm == kLightPointHoisted || is_cached(lm)) ? (k.B < kHoistMats ? k.B : kHoistMats) : 1;
   grid.z = (k.B + k.mats_per_cta - 1) / k.mats_per_cta;
+}
+
+// launch with `smem` bytes of dynamic shared memory (opt-in above 48 KB, once per kernel instantiation and device)
+template <void (*Kern)(CtKParams)>
+static void launch_dyn(const CtKParams& k, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  static std::atomic<uint64_t> configured{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(configured.load(std::memory_order_acquire) & bit)) {   // static + dynamic may exceed 48 KB before dynamic alone does
+    cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PBR_GC_MAX_BYTES);
+    configured.fetch_or(bit, std::memory_order_release);
+  }
+  Kern<<<grid, block, smem, st>>>(k);
 }
 
 // kernel workflow index: 0 metallic (1-channel map), 1 specular, 2 metallic with a 3-channel map
@@ -752,6 +891,8 @@ static void launch_fwd(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t s
   switch (light_mode(k)) {
     case kLightDirectional: ct_forward_kernel<WF, kLightDirectional><<<grid, block, 0, st>>>(k); break;
     case kLightPoint: ct_forward_kernel<WF, kLightPoint><<<grid, block, 0, st>>>(k); break;
+    case kLightPointCached: launch_dyn<ct_forward_kernel<WF, kLightPointCached>>(k, grid, block, geom_cache_bytes(k.flags.L, kLightPointCached), st); break;
+    case kLightPointCachedAll: launch_dyn<ct_forward_kernel<WF, kLightPointCachedAll>>(k, grid, block, geom_cache_bytes(k.flags.L, kLightPointCachedAll), st); break;
     default: ct_forward_kernel<WF, kLightPointHoisted><<<grid, block, 0, st>>>(k); break;
   }
 }
@@ -761,6 +902,8 @@ static void launch_bwd(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t s
   switch (light_mode(k)) {
     case kLightDirectional: ct_backward_kernel<WF, kLightDirectional><<<grid, block, 0, st>>>(k); break;
     case kLightPoint: ct_backward_kernel<WF, kLightPoint><<<grid, block, 0, st>>>(k); break;
+    case kLightPointCached: launch_dyn<ct_backward_kernel<WF, kLightPointCached>>(k, grid, block, geom_cache_bytes(k.flags.L, kLightPointCached), st); break;
+    case kLightPointCachedAll: launch_dyn<ct_backward_kernel<WF, kLightPointCachedAll>>(k, grid, block, geom_cache_bytes(k.flags.L, kLightPointCachedAll), st); break;
     default: ct_backward_kernel<WF, kLightPointHoisted><<<grid, block, 0, st>>>(k); break;
   }
 }
@@ -918,6 +1061,7 @@ uint64_t pbr_sizeof(int which) {
     case 11: return sizeof(PbrIndexDesc);
     case 12: return sizeof(PbrAdamMap);
     case 13: return sizeof(PbrAdamDesc);
+    case 14: return sizeof(PbrCtAdam);
     default: return 0;
   }
 }
@@ -952,6 +1096,34 @@ int pbr_ct_loss_fwd_bwd(const PbrCtDesc* desc, const PbrCtLoss* loss, const PbrC
   k.is_loss = 1;
   k.loss_scale = loss->loss_scale; k.loss_sum = loss->loss_sum;
   k.vec_ok = k.vec_ok && plane_vec_ok(loss->target) && (loss->target_sl % kTexels == 0);
+  return ct_dispatch(k, kernel_workflow(desc), true, (cudaStream_t)stream);
+}
+
+int pbr_ct_fit_step(const PbrCtDesc* desc, const PbrCtLoss* loss, const PbrCtAdam* adam, float* d_intensity,
+                    pbr_stream_t stream) {
+  CtKParams k{};
+  if (int rc = fill_ct_params(desc, k)) return rc;
+  if (!loss || !loss->target.ptr || !loss->loss_sum || !adam) return PBR_E_NULL;
+  // the maps are updated in place: a batch-broadcast map (sb == 0) would be written by every material
+  if (desc->B > 1 && (desc->albedo.sb == 0 || desc->roughness.sb == 0 || desc->metspec.sb == 0 || (desc->normal.ptr && desc->normal.sb == 0)))
+    return PBR_E_SHAPE;
+  const PbrPlane* mom[8] = {&adam->m_albedo, &adam->v_albedo, &adam->m_normal, &adam->v_normal,
+                            &adam->m_roughness, &adam->v_roughness, &adam->m_metspec, &adam->v_metspec};
+  for (int q = 0; q < 4; ++q) {
+    const bool need = q != 1 || desc->normal.ptr != nullptr;
+    if (need && (!mom[2 * q]->ptr || !mom[2 * q + 1]->ptr)) return PBR_E_NULL;
+    k.adam_m[q] = *mom[2 * q]; k.adam_v[q] = *mom[2 * q + 1];
+    k.vec_ok = k.vec_ok && plane_vec_ok(k.adam_m[q]) && plane_vec_ok(k.adam_v[q]);
+  }
+  k.d_intensity = d_intensity;
+  k.gsrc = loss->target; k.gsrc_sl = loss->target_sl;
+  k.is_loss = 1;
+  k.loss_scale = loss->loss_scale; k.loss_sum = loss->loss_sum;
+  k.vec_ok = k.vec_ok && plane_vec_ok(loss->target) && (loss->target_sl % kTexels == 0);
+  k.adam_on = 1;
+  k.adam_project = adam->project;
+  k.adam = AdamCoef{adam->step_size, adam->one_minus_beta1, adam->beta2, adam->one_minus_beta2, adam->bias2_sqrt, adam->eps};
+  k.force_generic = 1;   // the Adam epilogue lives in the generic kernels (any L)
   return ct_dispatch(k, kernel_workflow(desc), true, (cudaStream_t)stream);
 }
 

@@ -68,15 +68,74 @@ inline Linspace make_linspace(float start, float end, int n) {
 enum LightMode {
   kLightDirectional = 0,  // constant over the image: read from the stage
   kLightPoint = 1,        // computed per texel and per light
-  kLightPointHoisted = 2  // point light, L == 1: computed once per texel by the caller and reused for
+  kLightPointHoisted = 2, // point light, L == 1: computed once per texel by the caller and reused for
                           // every material of the batch the thread walks over (geometry does not
                           // depend on the material)
+  kLightPointCached = 3,  // point lights, L > 1: the caller computes the geometry of every light once per
+                          // texel, parks it in its own shared-memory slots (GeomCache) and the light loops
+                          // of all the materials it walks over read it back.  Caches l and h (6 fields).
+  kLightPointCachedAll = 4  // same with all 8 fields cached: for few lights, where the cache does not cost occupancy
 };
+PBR_HDC bool is_cached(int light_mode) { return light_mode == kLightPointCached || light_mode == kLightPointCachedAll; }
+// Fields: l (3), h (3) [, p5, att].  The fields that are not cached are recomputed from the plane position
+// (they live in the tolerant zone; l and h feed N.L / N.H and stay bit-exact).
+PBR_HDC int geom_fields(int light_mode) { return light_mode == kLightPointCachedAll ? 8 : 6; }
+
+// Per-thread geometry cache (kLightPointCached).  Field f of light l of lane-value i lives at
+// base[(l * kGeomFields + f) * fstride + i * stride]; `base` already points at the calling thread's slot,
+// `stride` is the thread count and `fstride` = lane-values per thread * stride, so a warp-level access touches
+// consecutive 8-byte words (conflict-free LDS.64).
+// A thread only ever reads what it wrote itself: no synchronisation.
+template <class V>
+struct GeomCache {
+  V* base;
+  int stride, fstride;
+};
+
+template <class V>
+PBR_HD V p5_from_half(V hx, V hy, V hz, float vx, float vy, float vz) {
+  V c = clamp01(xdot3(hx, hy, hz, splat<V>(vx), splat<V>(vy), splat<V>(vz)));
+  V omc = 1.0f - c;
+  V o2 = omc * omc;
+  return o2 * o2 * omc;
+}
+
+template <int kGeomFields, class V>
+PBR_HD void geom_cache_store(const GeomCache<V>& gc, int l, int i, const LightGeomT<V>& g) {
+  const int fs = gc.fstride;
+  V* q = gc.base + (l * kGeomFields) * fs + i * gc.stride;
+  q[0] = g.lx; q[fs] = g.ly; q[2 * fs] = g.lz;
+  q[3 * fs] = g.hx; q[4 * fs] = g.hy; q[5 * fs] = g.hz;
+  if (kGeomFields >= 7) q[6 * fs] = g.p5;
+  if (kGeomFields >= 8) q[7 * fs] = g.att;
+}
+
+template <int kGeomFields, class V>
+PBR_HD void geom_cache_load(const GeomCache<V>& gc, int l, int i, const float p[3], V x, float y, float vx, float vy,
+                            float vz, LightGeomT<V>& g) {
+  const int fs = gc.fstride;
+  const V* q = gc.base + (l * kGeomFields) * fs + i * gc.stride;
+  g.lx = q[0]; g.ly = q[fs]; g.lz = q[2 * fs];
+  g.hx = q[3 * fs]; g.hy = q[4 * fs]; g.hz = q[5 * fs];
+  if (kGeomFields >= 7) g.p5 = q[6 * fs];
+  else g.p5 = p5_from_half(g.hx, g.hy, g.hz, vx, vy, vz);
+  if (kGeomFields >= 8) {
+    g.att = q[7 * fs];
+  } else {
+    // 1/(d^2 + 1e-7), cooktorrance.py:140: tolerant zone (scales the colour linearly)
+    const float ly = p[1] + y;
+    const float yz = ly * ly + p[2] * p[2];
+    V Lx = splat<V>(p[0]) - x;
+    g.att = fast_rcp(Lx * Lx + (yz + kEps7));
+  }
+}
 
 template <int kLight, class V, int N>
 PBR_HD void light_geom(const CtStage& S, int l, const V (&x)[N], float y, const LightGeomT<V> (&hoisted)[N], int i,
-                       LightGeomT<V>& g) {
-  if (kLight == kLightPoint) {
+                       const GeomCache<V>& gc, LightGeomT<V>& g) {
+  if (is_cached(kLight)) {
+    geom_cache_load<geom_fields(kLight), V>(gc, l, i, S.light[l].p, x[i], y, S.vx, S.vy, S.vz, g);
+  } else if (kLight == kLightPoint) {
     point_light_geom(S.light[l].p[0], S.light[l].p[1], S.light[l].p[2], x[i], y, S.vx, S.vy, S.vz, g);
   } else if (kLight == kLightPointHoisted) {
     g = hoisted[i];
@@ -101,7 +160,7 @@ PBR_HD V encode_out_d(V c, bool return_srgb, V* d) {
 template <int kWorkflow, int kLight, class V, int N, class Emit>
 PBR_HD void ct_forward_group(const CtStage& S, const CtFlags& F, const V (&araw)[3][N], const V (&nraw)[3][N],
                              const V (&rough)[N], const V (&mraw)[3][N], const V (&x)[N], float y,
-                             const LightGeomT<V> (&hoisted)[N], Emit emit) {
+                             const LightGeomT<V> (&hoisted)[N], Emit emit, GeomCache<V> gc = GeomCache<V>()) {
   Texel<kWorkflow, V> t[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
@@ -122,7 +181,7 @@ PBR_HD void ct_forward_group(const CtStage& S, const CtFlags& F, const V (&araw)
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       LightGeomT<V> g;
-      light_geom<kLight, V, N>(S, l, x, y, hoisted, i, g);
+      light_geom<kLight, V, N>(S, l, x, y, hoisted, i, gc, g);
       LightFwd<V> f;
       V col[3];
       shade_light_fwd<kWorkflow>(t[i], g, S.light[l].inten, f, col);
@@ -152,6 +211,7 @@ PBR_HD void ct_forward_group(const CtStage& S, const CtFlags& F, const V (&araw)
 //        current, start loading the grad_out / target of light l" (l == L: rotate only).  gout(l) then reads the
 //        current buffer, which was requested one whole light iteration earlier.
 //   int_sink(l, g_int[3])       : per-light intensity gradient summed over the texels of the group.
+//   gc                          : kLightPointCached only, the calling thread's geometry cache.
 // Results: d_albedo/d_normal/d_met [3][N], d_rough[N].
 // ------------------------------------------------------------------------------------------------
 struct NoFetch {
@@ -162,7 +222,8 @@ template <int kWorkflow, int kLight, class V, int N, class Gout, class IntSink, 
 PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw)[3][N], const V (&nraw)[3][N],
                               const V (&rough)[N], const V (&mraw)[3][N], const V (&x)[N], float y,
                               const LightGeomT<V> (&hoisted)[N], Gout gout, IntSink int_sink, V (&d_albedo)[3][N],
-                              V (&d_normal)[3][N], V (&d_rough)[N], V (&d_met)[3][N], Fetch fetch = Fetch()) {
+                              V (&d_normal)[3][N], V (&d_rough)[N], V (&d_met)[3][N], Fetch fetch = Fetch(),
+                              GeomCache<V> gc = GeomCache<V>()) {
   Texel<kWorkflow, V> t[N];
   TexelGrad<V> tg[N];
 #pragma unroll
@@ -189,7 +250,7 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         LightGeomT<V> g;
-        light_geom<kLight, V, N>(S, l, x, y, hoisted, i, g);
+        light_geom<kLight, V, N>(S, l, x, y, hoisted, i, gc, g);
         LightFwd<V> f;
         V col[3];
         shade_light_fwd<kWorkflow>(t[i], g, S.light[l].inten, f, col);
@@ -221,7 +282,7 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
     V outv[3][N], slope[3][N], gl[3][N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      light_geom<kLight, V, N>(S, l, x, y, hoisted, i, g[i]);
+      light_geom<kLight, V, N>(S, l, x, y, hoisted, i, gc, g[i]);
       V col[3];
       shade_light_fwd<kWorkflow>(t[i], g[i], S.light[l].inten, f[i], col);
       if (!two_pass) {

@@ -14,6 +14,7 @@ loss sum and the gradient of the shared light intensities (`allreduce_loss_and_s
 
 from __future__ import annotations
 
+import ctypes
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -189,16 +190,108 @@ class FusedAdam:
             _cabi.check(lib.pbr_adam_step(_cabi.byref(d), _cabi.stream_ptr(device)), "pbr_adam_step")
 
 
+def fused_fit_step(
+    material: MaterialBase,
+    optimizer: FusedAdam,
+    target: torch.Tensor,
+    view_dir: torch.Tensor,
+    lights: torch.Tensor,
+    intensity: torch.Tensor,
+    light_type: str = "point",
+    light_size: Optional[float] = None,
+    return_srgb: bool = True,
+    multi_light: str = "per_light",
+    loss_scale: Optional[float] = None,
+    want_intensity_grad: bool = False,
+    scratch: Optional[Dict[str, torch.Tensor]] = None,
+) -> torch.Tensor:
+    """
+    Render + MSE + backward + Adam + projection in ONE kernel launch (pbr_ct_fit_step): the map gradients stay in
+    registers and the optimiser's pass over parameters and moments rides along the shading kernel.  Numerically the
+    same step as `fused_loss_step` followed by `optimizer.step(grads)`.
+
+    The optimiser must own exactly the maps the kernel shades (albedo, roughness, metallic | specular, and normal
+    if the material has one) - the very tensors stored in the material, contiguous, not batch-broadcast - with the
+    default projection for all of them or none at all.  Anything else: use `fit_step(..., fused=False)`.
+    Returns the device buffer [sum of squared errors, d_intensity(L*3)...] (not all-reduced).
+    """
+    lib = _cabi.load()
+    cfg, (albedo, normal, roughness, metspec), _leaf, device = _prepare(
+        material, material.device, view_dir, lights, intensity, light_type, light_size, return_srgb, multi_light
+    )
+    _cabi.require_cuda(target, "target")
+    target = target.contiguous()
+    expect = ((albedo.shape[0],) if cfg.batched else ()) + ((cfg.L,) if cfg.per_light else ()) + (3, *albedo.shape[-2:])
+    if tuple(target.shape) != expect:
+        raise ValueError(f"target has shape {tuple(target.shape)}, expected {expect}")
+    if loss_scale is None:
+        loss_scale = 1.0 / target.numel()
+    met_name = "metallic" if cfg.workflow == _cabi.WORKFLOW_METALLIC else "specular"
+    shaded = {"albedo": albedo, "roughness": roughness, met_name: metspec}
+    if normal is not None:
+        shaded["normal"] = normal
+    if set(optimizer.params) != set(shaded):
+        raise ValueError(f"fused_fit_step: the optimiser holds {sorted(optimizer.params)}, the kernel updates {sorted(shaded)}")
+    kinds = set()
+    for name, t in shaded.items():
+        p = optimizer.params[name]
+        if p.data_ptr() != t.data_ptr() or tuple(p.shape[-3:]) != tuple(t.shape[-3:]) or not t.is_contiguous():
+            raise ValueError(f"fused_fit_step: {name} is updated in place and must be the optimiser's own contiguous tensor")
+        pr, want = optimizer.project[name], DEFAULT_PROJECTION[name]
+        kinds.add(None if pr is None else (pr[0] == want[0] and (pr[0] == "normalize" or tuple(pr[1:3]) == tuple(want[1:3]))))
+    if kinds not in ({None}, {True}):
+        raise ValueError("fused_fit_step: projection must be the default for every map or None for every map")
+    scratch = scratch if scratch is not None else {}
+    red = scratch.get("buf")
+    if red is None or red.numel() != 1 + 3 * cfg.L:
+        red = torch.empty(1 + 3 * cfg.L, dtype=torch.float32, device=device)
+        scratch["buf"] = red
+    red.zero_()
+    keep: list = []
+    d = _fill_desc(cfg, albedo, normal, roughness, metspec, keep)
+    ls = _cabi.PbrCtLoss()
+    ls.target, ls.target_sl = _out_plane(target, cfg.per_light, cfg.batched)
+    ls.loss_scale = float(loss_scale)
+    ls.loss_sum = red.data_ptr()
+    optimizer.step_count += 1
+    b1, b2 = optimizer.betas
+    a = _cabi.PbrCtAdam()
+    for key, name in (("albedo", "albedo"), ("normal", "normal"), ("roughness", "roughness"), ("metspec", met_name)):
+        if name in optimizer.state:
+            m, v = optimizer.state[name]
+            setattr(a, "m_" + key, _cabi.plane(m))
+            setattr(a, "v_" + key, _cabi.plane(v))
+    a.step_size = optimizer.lr / (1.0 - b1 ** optimizer.step_count)
+    a.one_minus_beta1, a.beta2, a.one_minus_beta2 = 1.0 - b1, b2, 1.0 - b2
+    a.bias2_sqrt = (1.0 - b2 ** optimizer.step_count) ** 0.5
+    a.eps = optimizer.eps
+    a.project = 1 if kinds == {True} else 0
+    d_int = ctypes.c_void_p(red[1:].data_ptr()) if want_intensity_grad else None
+    with torch.cuda.device(device):
+        _cabi.check(
+            lib.pbr_ct_fit_step(_cabi.byref(d), _cabi.byref(ls), _cabi.byref(a), d_int, _cabi.stream_ptr(device)),
+            "pbr_ct_fit_step",
+        )
+    return red
+
+
 def fit_step(material: MaterialBase, optimizer: FusedAdam, target: torch.Tensor, view_dir, lights, intensity,
              light_type: str = "point", light_size: Optional[float] = None, multi_light: str = "per_light",
-             scratch: Optional[Dict[str, torch.Tensor]] = None, global_numel: Optional[int] = None) -> torch.Tensor:
+             scratch: Optional[Dict[str, torch.Tensor]] = None, global_numel: Optional[int] = None,
+             fused: bool = False) -> torch.Tensor:
     """
     One step of the sharded inverse-rendering fit on this rank's materials: fused render + MSE + backward
     (pbr_ct_loss_fwd_bwd), ONE all-reduce of the loss buffer, fused Adam + projection (pbr_adam_step).
+    `fused=True`: all of it in one launch (pbr_ct_fit_step, see fused_fit_step); the all-reduce then only serves
+    the reported loss.
     `global_numel`: element count of the target over ALL ranks (the MSE denominator); default: this rank's.
     Returns the all-reduced buffer [sum of squared errors, ...] (device tensor; multiply [0] by 1/global_numel).
     """
     numel = global_numel if global_numel is not None else target.numel()
+    if fused:
+        buf = fused_fit_step(material, optimizer, target, view_dir, lights, intensity, light_type, light_size,
+                             multi_light=multi_light, loss_scale=1.0 / numel, scratch=scratch)
+        return allreduce_loss_and_shared(buf)
     buf, grads = fused_loss_step(material, target, view_dir, lights, intensity, light_type, light_size,
                                  multi_light=multi_light, loss_scale=1.0 / numel, out=scratch)
     allreduce_loss_and_shared(buf)

@@ -17,6 +17,19 @@ struct Dims {
   int B, H, W, L;
 };
 
+// kLightPointCached: what the kernels' prologue does per texel pair, with a private cache
+template <int LIGHT, class V>
+GeomCache<V> fill_cache(const CtStage& S, int L, V x, float y, V* store) {
+  GeomCache<V> gc{store, 1, 1};
+  if (is_cached(LIGHT))
+    for (int l = 0; l < L; ++l) {
+      LightGeomT<V> g;
+      point_light_geom(S.light[l].p[0], S.light[l].p[1], S.light[l].p[2], x, y, S.vx, S.vy, S.vz, g);
+      geom_cache_store<geom_fields(LIGHT), V>(gc, l, 0, g);
+    }
+  return gc;
+}
+
 // One call shades Lanes<V>::n horizontally adjacent texels (V = float: 1, V = f2: 2, the packing the
 // CUDA kernels use); at a ragged right edge the second lane repeats the last column and is dropped.
 template <int WF, bool HASN, int LIGHT, class V>
@@ -50,7 +63,8 @@ void fwd_impl(const Dims& d, const CtStage& S, const CtFlags& F, const float* al
         LightGeomT<V> hg[1];
         if (LIGHT == kLightPointHoisted)
           point_light_geom(S.light[0].p[0], S.light[0].p[1], S.light[0].p[2], x[0], y, S.vx, S.vy, S.vz, hg[0]);
-        ct_forward_group<WF, LIGHT, V, 1>(S, F, a, n, r, m, x, y, hg, emit);
+        V store[PBR_MAX_LIGHTS * 8];
+        ct_forward_group<WF, LIGHT, V, 1>(S, F, a, n, r, m, x, y, hg, emit, fill_cache<LIGHT, V>(S, d.L, x[0], y, store));
       }
 }
 
@@ -102,7 +116,9 @@ void bwd_impl(const Dims& d, const CtStage& S, const CtFlags& F, const float* al
         LightGeomT<V> hg[1];
         if (LIGHT == kLightPointHoisted)
           point_light_geom(S.light[0].p[0], S.light[0].p[1], S.light[0].p[2], x[0], y, S.vx, S.vy, S.vz, hg[0]);
-        ct_backward_group<WF, LIGHT, V, 1>(S, F, a, n, r, m, x, y, hg, gout, sink, da, dn, dr, dm);
+        V store[PBR_MAX_LIGHTS * 8];
+        ct_backward_group<WF, LIGHT, V, 1>(S, F, a, n, r, m, x, y, hg, gout, sink, da, dn, dr, dm, NoFetch(),
+                                           fill_cache<LIGHT, V>(S, d.L, x[0], y, store));
         for (int k = 0; k < live; ++k) {
           for (int c = 0; c < 3; ++c) d_albedo[(b * 3 + c) * HW + o[k]] = lane_get(da[c][0], k);
           if (HASN && d_normal)
@@ -122,32 +138,29 @@ void make_stage(const Dims& d, int light_type, float light_size, const float* vi
   for (int l = 0; l < d.L; ++l) stage_light(l, lights, inten, light_type == 1, S.vx, S.vy, S.vz, S.light[l]);
 }
 
-// light mode: directional / point / point-hoisted (the kernels pick the hoisted variant for L == 1).
-// `force_generic` bit 0: generic light mode; bit 1: V = f2 (two texels per call, the packing of the CUDA kernels).
-#define DISPATCH_V(fn, V, ...)                                                             \
-  do {                                                                                      \
-    int lm = light_type == 1 ? ((L == 1 && !(force_generic & 1)) ? 2 : 1) : 0;              \
-    int key = (workflow * 2 + (normal != nullptr)) * 3 + lm;                                \
-    switch (key) {                                                                          \
-      case 0: fn<0, false, 0, V>(__VA_ARGS__); break;                                       \
-      case 1: fn<0, false, 1, V>(__VA_ARGS__); break;                                       \
-      case 2: fn<0, false, 2, V>(__VA_ARGS__); break;                                       \
-      case 3: fn<0, true, 0, V>(__VA_ARGS__); break;                                        \
-      case 4: fn<0, true, 1, V>(__VA_ARGS__); break;                                        \
-      case 5: fn<0, true, 2, V>(__VA_ARGS__); break;                                        \
-      case 6: fn<1, false, 0, V>(__VA_ARGS__); break;                                       \
-      case 7: fn<1, false, 1, V>(__VA_ARGS__); break;                                       \
-      case 8: fn<1, false, 2, V>(__VA_ARGS__); break;                                       \
-      case 9: fn<1, true, 0, V>(__VA_ARGS__); break;                                        \
-      case 10: fn<1, true, 1, V>(__VA_ARGS__); break;                                       \
-      case 11: fn<1, true, 2, V>(__VA_ARGS__); break;                                       \
-      case 12: fn<2, false, 0, V>(__VA_ARGS__); break;                                      \
-      case 13: fn<2, false, 1, V>(__VA_ARGS__); break;                                      \
-      case 14: fn<2, false, 2, V>(__VA_ARGS__); break;                                      \
-      case 15: fn<2, true, 0, V>(__VA_ARGS__); break;                                       \
-      case 16: fn<2, true, 1, V>(__VA_ARGS__); break;                                       \
-      case 17: fn<2, true, 2, V>(__VA_ARGS__); break;                                       \
-    }                                                                                       \
+// light mode: directional / point / point-hoisted (the kernels pick the hoisted variant for L == 1) / point-cached
+// (the kernels pick it for L > 1 when a thread walks over several materials).
+// `force_generic` bit 0: generic light mode; bit 1: V = f2 (two texels per call, the packing of the CUDA kernels);
+// bit 2: point lights with L > 1 go through the geometry cache (kLightPointCached); bits 2+3: kLightPointCachedAll.
+#define DISPATCH_LM(fn, WF, HN, V, ...)                                  \
+  switch (lm) {                                                           \
+    case 0: fn<WF, HN, 0, V>(__VA_ARGS__); break;                         \
+    case 1: fn<WF, HN, 1, V>(__VA_ARGS__); break;                         \
+    case 2: fn<WF, HN, 2, V>(__VA_ARGS__); break;                         \
+    case 3: fn<WF, HN, 3, V>(__VA_ARGS__); break;                         \
+    default: fn<WF, HN, 4, V>(__VA_ARGS__); break;                        \
+  }
+#define DISPATCH_V(fn, V, ...)                                                                            \
+  do {                                                                                                     \
+    int lm = light_type == 1 ? ((L == 1 && !(force_generic & 1)) ? 2 : ((L > 1 && (force_generic & 4)) ? ((force_generic & 8) ? 4 : 3) : 1)) : 0; \
+    switch (workflow * 2 + (normal != nullptr)) {                                                          \
+      case 0: DISPATCH_LM(fn, 0, false, V, __VA_ARGS__) break;                                             \
+      case 1: DISPATCH_LM(fn, 0, true, V, __VA_ARGS__) break;                                              \
+      case 2: DISPATCH_LM(fn, 1, false, V, __VA_ARGS__) break;                                             \
+      case 3: DISPATCH_LM(fn, 1, true, V, __VA_ARGS__) break;                                              \
+      case 4: DISPATCH_LM(fn, 2, false, V, __VA_ARGS__) break;                                             \
+      case 5: DISPATCH_LM(fn, 2, true, V, __VA_ARGS__) break;                                              \
+    }                                                                                                      \
   } while (0)
 #define DISPATCH(fn, ...)                                                                   \
   do {                                                                                      \

@@ -123,6 +123,9 @@ def _random_case(seed, B, H, W, L, workflow="metallic", rough_lo=0.2, normal=Tru
     (19, 9, 256, 1, True, "metallic"),    # streamed path: 4 rows per tile, H % 4 != 0, B > one CTA's walk
     (2, 2, 1536, 1, True, "specular"),    # streamed path: second strip half empty
     (3, 5, 72, 1, False, "metallic"),     # streamed path: per_light flag with a single light, narrow image
+    (19, 9, 40, 6, False, "metallic"),    # geometry cache (l, h cached): B > one CTA's walk, per-light outputs
+    (18, 8, 33, 3, True, "specular"),     # geometry cache (all 8 fields): two-pass accumulate backward, ragged W
+    (17, 4, 24, 12, True, "metallic"),    # geometry cache at 12 lights
 ])
 def test_against_oracle_seeded(B, H, W, L, acc, wf, ct_path):
     """Fresh seeded inputs (not in the fixtures) against the oracle run on the host."""
@@ -585,3 +588,69 @@ def test_fused_adam_matches_torch_adam_and_fit_converges():
         buf = fit_step(pred, opt, target, view, lights, inten, "point", 1.0, scratch=scratch)
         losses.append(float(buf[0]) / target.numel())
     assert losses[-1] < 0.25 * losses[0], losses[::8]
+
+
+@pytest.mark.parametrize("L,wf,normal,project", [(1, "metallic", True, True), (3, "metallic", True, True),
+                                                 (6, "specular", True, True), (3, "metallic", False, False)])
+def test_one_launch_fit_step_equals_loss_kernel_plus_adam_kernel(L, wf, normal, project):
+    """pbr_ct_fit_step (render + MSE + backward + Adam + projection in one launch, gradients in registers) must walk
+    the same trajectory as pbr_ct_loss_fwd_bwd followed by pbr_adam_step: same formulas on the same fp32 gradient
+    values (tolerance 2e-6 relative for multiply-add contraction differences between the two instantiations)."""
+    from pypbr_b200.fit import FusedAdam, fit_step
+    from pypbr_b200.materials import BasecolorMetallicMaterial, DiffuseSpecularMaterial
+    from pypbr_b200.models import CookTorranceBRDF
+
+    maps, lights, inten, _ = _random_case(77 + L, 3, 27, 44, L, workflow=wf)   # ragged width: scalar tail path
+    if not normal:
+        maps.pop("normal")
+    view = torch.tensor([0.1, -0.05, 1.0])
+    gt, _ = _material(maps, dict(light_type="point"))
+    with torch.no_grad():
+        target = CookTorranceBRDF("point", multi_light="per_light")(gt, view, lights, inten, 1.0)
+    cls = BasecolorMetallicMaterial if wf == "metallic" else DiffuseSpecularMaterial
+    runs = []
+    for fused in (False, True):
+        pred = cls(albedo_is_srgb=True, device=DEV)
+        leaves = {}
+        for k, v in maps.items():
+            t = torch.from_numpy(v) if isinstance(v, np.ndarray) else v
+            leaves[k] = (t * 0.7 + 0.1 if k != "normal" else t).contiguous().to(DEV).clone()
+            pred._maps[k] = leaves[k]
+        if not normal:
+            pred._maps["normal"] = None
+        opt = FusedAdam(leaves, lr=0.03, project=None if project else {k: None for k in leaves})
+        losses = []
+        for _ in range(4):
+            buf = fit_step(pred, opt, target, view, lights, inten, "point", 1.0, fused=fused)
+            losses.append(float(buf[0]))
+        runs.append((leaves, opt.state, losses))
+    (p0, s0, l0), (p1, s1, l1) = runs
+    assert l1[-1] < l1[0]
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-5 * abs(a)
+    for k in p0:
+        for a, b in ((p0[k], p1[k]), (s0[k][0], s1[k][0]), (s0[k][1], s1[k][1])):
+            err = (a - b).abs()
+            # an Adam step is lr-sized whatever the gradient: a one-ulp gradient difference near zero can flip a step,
+            # so allow a handful of outliers bounded by the step size
+            bad = err > 2e-6 * a.abs() + 1e-7
+            assert float(bad.float().mean()) < 1e-3, (k, float(err.max()))
+            assert float(err.max()) <= 0.07, (k, float(err.max()))
+
+
+def test_fit_step_rejects_what_the_one_launch_path_cannot_update_in_place():
+    from pypbr_b200.fit import FusedAdam, fused_fit_step
+    from pypbr_b200.models import CookTorranceBRDF
+
+    maps, lights, inten, _ = _random_case(5, 2, 16, 16, 2)
+    view = torch.tensor([0.0, 0.0, 1.0])
+    mat, leaves = _material(maps, dict(light_type="point"))
+    with torch.no_grad():
+        target = CookTorranceBRDF("point", multi_light="per_light")(mat, view, lights, inten, 1.0)
+    with pytest.raises(ValueError):   # the optimiser misses maps the kernel updates
+        fused_fit_step(mat, FusedAdam({"albedo": leaves["albedo"]}), target, view, lights, inten)
+    with pytest.raises(ValueError):   # mixed projection
+        fused_fit_step(mat, FusedAdam(leaves, project={"albedo": None}), target, view, lights, inten)
+    other = {k: v.clone() for k, v in leaves.items()}
+    with pytest.raises(ValueError):   # not the material's own tensors
+        fused_fit_step(mat, FusedAdam(other), target, view, lights, inten)

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_cabi.lib_path())
     for name in declared:
         assert hasattr(lib, name), name
-    assert _cabi.load().pbr_abi_version() == _cabi.ABI_VERSION == 3
+    assert _cabi.load().pbr_abi_version() == _cabi.ABI_VERSION == 4
 
 
 def test_struct_layouts_match_header_sizes():

@@ -35,7 +35,7 @@ def _args(z):
     return args, maps, ms, wf, L, (a, view, lights, inten)
 
 
-@pytest.mark.parametrize("generic", [0, 1, 2, 3])  # bit 0: generic light mode, bit 1: two texels per call (f2 lanes)
+@pytest.mark.parametrize("generic", [0, 1, 2, 3, 5, 7, 15])  # bit 0: generic light mode, bit 1: two texels per call (f2 lanes), bit 2: geometry cache for L > 1, bit 3: all 8 fields cached
 @pytest.mark.parametrize("name", golden_ct_cases())
 def test_forward_matches_golden(hostsim, name, generic):
     z = load_golden(name)
@@ -50,7 +50,7 @@ def test_forward_matches_golden(hostsim, name, generic):
     assert e_us <= 2 * e_ref + 1e-6
 
 
-@pytest.mark.parametrize("generic", [0, 1, 2, 3])  # bit 0: generic light mode, bit 1: two texels per call (f2 lanes)
+@pytest.mark.parametrize("generic", [0, 1, 2, 3, 5, 7, 15])  # bit 0: generic light mode, bit 1: two texels per call (f2 lanes), bit 2: geometry cache for L > 1, bit 3: all 8 fields cached
 @pytest.mark.parametrize("name", golden_ct_cases())
 def test_backward_matches_golden(hostsim, name, generic):
     z = load_golden(name)

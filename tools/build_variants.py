@@ -25,6 +25,14 @@ VARIANTS = {
     "g_t256x2_f3b1": v(ct_threads=256, fwd_min_ctas=3, bwd_min_ctas=1),
     "g_t64x2_f8b6": v(ct_threads=64, fwd_min_ctas=8, bwd_min_ctas=6),
     "g_t64x2_f10b5": v(ct_threads=64, fwd_min_ctas=10, bwd_min_ctas=5),
+    # geometry cache of the multi-light kernels (point lights, L > 1): fields cached / off / CTAs per SM
+    "gc_off": ["-DPBR_GC_MAX_BYTES=0"],
+    "gc7": ["-DPBR_GC_FIELDS=7"],
+    "gc8": ["-DPBR_GC_FIELDS=8"],
+    "gc6_f3b2": v(fwd_min_ctas=3, bwd_min_ctas=2),
+    "gc8_f3b2": ["-DPBR_GC_FIELDS=8"] + v(fwd_min_ctas=3, bwd_min_ctas=2),
+    "gc6_t64": v(ct_threads=64, fwd_min_ctas=8, bwd_min_ctas=6),
+    "gc6_m32": v(hoist_mats=32),
     # memory pipeline only (no shading math): the floor of the TMA-in / STG-out design
     "nomath": ["-DPBR_DBG_NOMATH"],
 }

@@ -93,6 +93,11 @@ for path in paths:
         assert rc == 0, rc
 
     times = {}
+    try:
+        fwd(); bwd()
+    except AssertionError as e:
+        print(f"{name:20s} launch failed rc={e}", flush=True)
+        continue
     for label, fn in (("fwd", fwd), ("bwd", bwd)):
         for _ in range(3):
             fn()
