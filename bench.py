@@ -239,6 +239,7 @@ def run_ours(args, cfg):
 
     B, H, W, L, per_light = cfg["B"], cfg["H"], cfg["W"], cfg["L"], cfg["per_light"]
     fused_fit = args.config == "c5"
+    one_launch = fused_fit and args.fit == "one-launch"
     maps = synth_maps(B, H, W, dev, 1000 * 2 + rank)
     mat = BasecolorMetallicMaterial(albedo_is_srgb=True, device=dev)
     leaves = []
@@ -272,6 +273,14 @@ def run_ours(args, cfg):
             # one full step of the sharded fit: fused render + MSE + backward, ONE all-reduce, fused Adam + projection
             e0, e1, e2 = ev(), ev(), ev()
             e0.record()
+            if one_launch:
+                # ... all of it in ONE launch (pbr_ct_fit_step: Adam + projection in the loss kernel's epilogue)
+                fit_step(mat, adam, target, view, lights, inten, "point", 1.0, scratch=bufs,
+                         global_numel=target.numel() * world, fused=True)
+                e1.record()
+                if record:
+                    bwd_ms.append((e0, e1))
+                return
             buf, grads = fused_loss_step(mat, target, view, lights, inten, "point", 1.0, multi_light="per_light",
                                          loss_scale=1.0 / (target.numel() * world), out=bufs)
             e1.record()
@@ -322,7 +331,12 @@ def run_ours(args, cfg):
     peak, peak_src = measured_peak()
     texels = B * H * W
     bwd_avg = sum(a.elapsed_time(b) for a, b in bwd_ms) / len(bwd_ms)
-    if fused_fit:
+    if one_launch:
+        # maps in (32) + per-light targets (12 L) + maps out (32) + both Adam moments of 8 planes read and written (64)
+        kbytes = texels * (32 + 12 * L + 32 + 64)
+        kname = "ct_backward_kernel (fused loss + Adam epilogue; includes the loss all-reduce when n_gpus > 1)"
+        fwd_avg = None
+    elif fused_fit:
         kbytes = texels * (32 + 12 * L + 32)
         kname = "ct_backward_kernel (fused loss)"
         fwd_avg = None
@@ -331,11 +345,11 @@ def run_ours(args, cfg):
         kbytes = texels * (BWD_BYTES if not per_light else 64 + 12 * L)
         kname = "ct_backward_kernel"
     achieved = kbytes / (bwd_avg * 1e-3) / 1e9
-    tr = measured_traffic(f"{args.config}:backward")
+    tr = measured_traffic(f"{args.config}:backward" + (":two-kernel" if fused_fit and not one_launch else ""))
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (tr or {}).get("bytes"), "traffic_source": (tr or {}).get("source"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": kbytes, "kernel_ms": bwd_avg}
-    if fused_fit:
+    if fused_fit and not one_launch:
         a_avg = sum(a.elapsed_time(b) for a, b in adam_ms) / len(adam_ms)
         ab = texels * 8 * 28   # 8 parameter planes: read p, g, m, v and write p, m, v
         roofline["adam"] = {"kernel": "adam_kernel (+ the loss all-reduce when n_gpus > 1)", "kernel_ms": a_avg,
@@ -435,7 +449,7 @@ def run_ours(args, cfg):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["workload"], "per_gpu_batch": B, "H": H, "W": W, "lights": L,
-                       "mode": "per_light fused loss + Adam" if fused_fit else "accumulate", "parallelism": f"batch-shard x{world}",
+                       "mode": ("per_light fused loss + Adam, " + args.fit) if fused_fit else "accumulate", "parallelism": f"batch-shard x{world}",
                        "l2": "inputs (2.1 GB per GPU) exceed the 126 MB L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk.summary(),
@@ -668,6 +682,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(list(CONFIGS) + ["c4", "aux"]))
+    ap.add_argument("--fit", default="one-launch", choices=["one-launch", "two-kernel"],
+                    help="c5: pbr_ct_fit_step (Adam in the loss kernel's epilogue) or pbr_ct_loss_fwd_bwd + pbr_adam_step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

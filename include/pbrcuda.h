@@ -93,6 +93,11 @@ typedef struct PbrCtGrads {
   PbrPlane d_roughness;     /* 1 ch */
   PbrPlane d_metspec;       /* 1 or 3 ch */
   float* d_intensity;       /* device, L*3, ACCUMULATED with atomics: caller zero-fills; may be NULL */
+  /* Gradients of the shared geometry parameters, which the reference delivers through plain autograd
+     (cooktorrance.py:95 view_dir, :125-140 light direction / position).  Device, ACCUMULATED with atomics (caller
+     zero-fills), may be NULL.  Requesting either selects the generic kernels with per-texel light geometry. */
+  float* d_lights;          /* L*3: w.r.t. PbrCtDesc.lights as passed (raw direction or position) */
+  float* d_view;            /* 3:   w.r.t. PbrCtDesc.view as passed (not normalised) */
 } PbrCtGrads;
 
 /*

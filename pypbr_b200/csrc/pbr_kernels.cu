@@ -150,6 +150,8 @@ struct CtKParams {
   int64_t gsrc_sl;
   PbrPlane d_albedo, d_normal, d_roughness, d_metspec;
   float* d_intensity;
+  float* d_lights;       // L*3: d/d light position (point) or raw direction (directional); geometry-gradient kernels
+  float* d_view;         // 3:   d/d raw view direction
   float loss_scale;
   float* loss_sum;
   // fused fit step (pbr_ct_fit_step): the epilogue applies Adam + projection to the maps in place instead of
@@ -353,11 +355,31 @@ __device__ __forceinline__ float warp_sum(float v) {
 #endif
 constexpr int bwd_min_ctas(int light_mode) { return light_mode == kLightPointCached ? PBR_BWD_CACHED_MIN_CTAS : PBR_BWD_MIN_CTAS; }
 
-template <int WF, int kLight>
-__global__ void __launch_bounds__(kCtThreads, bwd_min_ctas(kLight)) ct_backward_kernel(const __grid_constant__ CtKParams p) {
+// Sink of the geometry gradients (kGeom kernels): warp shuffle -> shared atomics, flushed once per CTA.
+struct CtaGeomSink {
+  static constexpr bool kOn = true;
+  float* s_geo;   // [L][3] lights, then [3] view
+  int L, tid;
+  float live;
+  __device__ __forceinline__ void add(int slot, const float (&g)[3]) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float sum = warp_sum(g[c] * live);
+      if ((tid & 31) == 0) atomicAdd(&s_geo[3 * slot + c], sum);
+    }
+  }
+  __device__ __forceinline__ void light(int l, const float (&g)[3]) const { add(l, g); }
+  __device__ __forceinline__ void view(const float (&g)[3]) const { add(L, g); }
+};
+
+// kGeom: also d/d(light position | direction) and d/d(view direction) (PbrCtGrads.d_lights / d_view), which the
+// reference delivers through plain autograd (cooktorrance.py:95,125-140).  Uncached per-texel light modes only.
+template <int WF, int kLight, bool kGeom = false>
+__global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) ct_backward_kernel(const __grid_constant__ CtKParams p) {
   constexpr int G = PBR_BWD_GROUP;
   __shared__ CtStage S;
   __shared__ float s_int[PBR_MAX_LIGHTS * 3];
+  __shared__ float s_geo[kGeom ? (PBR_MAX_LIGHTS + 1) * 3 : 1];
   __shared__ float s_loss[kCtThreads / 32];
   __shared__ __align__(16) float s_ring[kRing * 3 * kCtThreads * kLanes * PBR_BWD_GROUP];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -366,10 +388,13 @@ __global__ void __launch_bounds__(kCtThreads, bwd_min_ctas(kLight)) ct_backward_
   if (int_grad) {
     for (int i = tid; i < p.flags.L * 3; i += kCtThreads) s_int[i] = 0.0f;
   }
+  if (kGeom) {
+    for (int i = tid; i < (p.flags.L + 1) * 3; i += kCtThreads) s_geo[i] = 0.0f;
+  }
   stage_params(p, S);  // ends with __syncthreads()
   const Where w = locate_n<kCtTexels>(p.H, p.W, p.vec_ok != 0);
   const float live = w.active ? 1.0f : 0.0f;
-  if (!w.active && !int_grad && !is_loss) return;  // nothing to reduce: edge threads may leave
+  if (!w.active && !int_grad && !is_loss && !kGeom) return;  // nothing to reduce: edge threads may leave
 
   V x[kSlots];
   float y;
@@ -463,7 +488,12 @@ __global__ void __launch_bounds__(kCtThreads, bwd_min_ctas(kLight)) ct_backward_
       V da[3][G], dn[3][G], dr[G], dm[3][G];
       GeomCache<V> gcs = gc;
       gcs.base += s * gc.stride;
-      ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs);
+      if constexpr (kGeom) {
+        ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs,
+                                            CtaGeomSink{s_geo, p.flags.L, tid, live});
+      } else {
+        ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs);
+      }
 #pragma unroll
       for (int c = 0; c < 3; ++c) { unpair_to<G>(da[c], s, d_albedo[c]); unpair_to<G>(dn[c], s, d_normal[c]); unpair_to<G>(dm[c], s, d_met[c]); }
       unpair_to<G>(dr, s, d_rough);
@@ -545,7 +575,29 @@ __global__ void __launch_bounds__(kCtThreads, bwd_min_ctas(kLight)) ct_backward_
     float sum = warp_sum(loss_local * live);
     if ((tid & 31) == 0) s_loss[tid >> 5] = sum;
   }
-  if (is_loss || int_grad) __syncthreads();
+  if (is_loss || int_grad || kGeom) __syncthreads();
+  if (kGeom) {
+    // one thread per light (and one for the view) turns the CTA's partial sums into gradients of the RAW parameters:
+    // the Jacobians of F.normalize(dir) / F.normalize(view) are constant over the image, hence applied here, once
+    const float* view = p.view_dev ? p.view_dev : p.view;
+    const float* lights = p.lights_dev ? p.lights_dev : p.lights;
+    if (tid <= p.flags.L) {
+      const float g[3] = {s_geo[3 * tid], s_geo[3 * tid + 1], s_geo[3 * tid + 2]};
+      float o[3] = {g[0], g[1], g[2]};
+      float* dst = nullptr;
+      if (tid == p.flags.L) {
+        normalize_bwd(view, g, o);
+        dst = p.d_view;
+      } else {
+        if (!p.flags.point) normalize_bwd(lights + 3 * tid, g, o);
+        dst = p.d_lights ? p.d_lights + 3 * tid : nullptr;
+      }
+      if (dst) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(dst + c, o[c]);
+      }
+    }
+  }
   if (is_loss && tid == 0) {
     float sum = 0.0f;
     const int nw = (blockDim.x * blockDim.y + 31) >> 5;
@@ -851,6 +903,7 @@ static bool geom_cache_disabled() {
 
 static int light_mode(const CtKParams& k) {
   if (!k.flags.point) return kLightDirectional;
+  if (k.d_lights || k.d_view) return kLightPoint;   // geometry gradients need the per-texel intermediates
   if (k.flags.L == 1) return kLightPointHoisted;
   if (k.B >= 2 && !geom_cache_disabled()) {
     if (k.flags.L <= PBR_GC_ALL_MAX_LIGHTS) return kLightPointCachedAll;
@@ -899,6 +952,11 @@ static void launch_fwd(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t s
 
 template <int WF>
 static void launch_bwd(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t st) {
+  if (k.d_lights || k.d_view) {   // geometry gradients: the uncached per-texel light modes
+    if (k.flags.point) ct_backward_kernel<WF, kLightPoint, true><<<grid, block, 0, st>>>(k);
+    else ct_backward_kernel<WF, kLightDirectional, true><<<grid, block, 0, st>>>(k);
+    return;
+  }
   switch (light_mode(k)) {
     case kLightDirectional: ct_backward_kernel<WF, kLightDirectional><<<grid, block, 0, st>>>(k); break;
     case kLightPoint: ct_backward_kernel<WF, kLightPoint><<<grid, block, 0, st>>>(k); break;
@@ -912,6 +970,8 @@ static int fill_grads(const PbrCtGrads* g, CtKParams& k) {
   if (!g) return PBR_E_NULL;
   k.d_albedo = g->d_albedo; k.d_normal = g->d_normal; k.d_roughness = g->d_roughness; k.d_metspec = g->d_metspec;
   k.d_intensity = g->d_intensity;
+  k.d_lights = g->d_lights; k.d_view = g->d_view;
+  if (k.d_lights || k.d_view) k.force_generic = 1;
   k.vec_ok = k.vec_ok && plane_vec_ok(g->d_albedo) && plane_vec_ok(g->d_normal) && plane_vec_ok(g->d_roughness) &&
              plane_vec_ok(g->d_metspec);
   return PBR_OK;

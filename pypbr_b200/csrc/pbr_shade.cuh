@@ -217,13 +217,30 @@ PBR_HD void ct_forward_group(const CtStage& S, const CtFlags& F, const V (&araw)
 struct NoFetch {
   PBR_HD void operator()(int) const {}
 };
+//   geom_sink.light(l, g[3])    : (GeomSink != NoGeomSink only) gradient w.r.t. the position of point light l, or
+//        w.r.t. the UNIT direction of directional light l, summed over the texels of the group;
+//   geom_sink.view(g[3])        : gradient w.r.t. the UNIT view direction, summed over the group's texels and lights.
+struct NoGeomSink {
+  static constexpr bool kOn = false;
+  PBR_HD void light(int, const float (&)[3]) const {}
+  PBR_HD void view(const float (&)[3]) const {}
+};
 
-template <int kWorkflow, int kLight, class V, int N, class Gout, class IntSink, class Fetch = NoFetch>
+template <int kWorkflow, int kLight, class V, int N, class Gout, class IntSink, class Fetch = NoFetch,
+          class GeomSink = NoGeomSink>
 PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw)[3][N], const V (&nraw)[3][N],
                               const V (&rough)[N], const V (&mraw)[3][N], const V (&x)[N], float y,
                               const LightGeomT<V> (&hoisted)[N], Gout gout, IntSink int_sink, V (&d_albedo)[3][N],
                               V (&d_normal)[3][N], V (&d_rough)[N], V (&d_met)[3][N], Fetch fetch = Fetch(),
-                              GeomCache<V> gc = GeomCache<V>()) {
+                              GeomCache<V> gc = GeomCache<V>(), GeomSink geom_sink = GeomSink()) {
+  constexpr bool kGeom = GeomSink::kOn;
+  static_assert(!kGeom || kLight == kLightDirectional || kLight == kLightPoint,
+                "geometry gradients run on the uncached per-texel light modes");
+  V g_view[kGeom ? N : 1][3];
+  if (kGeom) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) g_view[i][0] = g_view[i][1] = g_view[i][2] = splat<V>(0.0f);
+  }
   Texel<kWorkflow, V> t[N];
   TexelGrad<V> tg[N];
 #pragma unroll
@@ -298,22 +315,34 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
         for (int i = 0; i < N; ++i) gl[c][i] *= slope[c][i];
     }
     float gi_sum[3] = {0.0f, 0.0f, 0.0f};
+    float glt_sum[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const V gc[3] = {two_pass ? g_tot[0][i] : gl[0][i], two_pass ? g_tot[1][i] : gl[1][i],
-                       two_pass ? g_tot[2][i] : gl[2][i]};
+      const V gcol[3] = {two_pass ? g_tot[0][i] : gl[0][i], two_pass ? g_tot[1][i] : gl[1][i],
+                         two_pass ? g_tot[2][i] : gl[2][i]};
       V gi[3];
-      shade_light_bwd<kWorkflow>(t[i], g[i], S.light[l].inten, f[i], gc, tg[i], gi);
+      GeomGrad<V> gg;
+      shade_light_bwd<kWorkflow, kGeom>(t[i], g[i], S.light[l].inten, f[i], gcol, tg[i], gi, &gg);
 #pragma unroll
       for (int c = 0; c < 3; ++c) gi_sum[c] += lane_sum(gi[c]);
+      if (kGeom) {
+        V glt[3];
+        light_geom_bwd<kLight == kLightPoint>(g[i], gg, S.light[l].p, x[i], y, S.vx, S.vy, S.vz, glt, g_view[i]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) glt_sum[c] += lane_sum(glt[c]);
+      }
     }
     int_sink(l, gi_sum);
+    if (kGeom) geom_sink.light(l, glt_sum);
   }
 
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    V da[3], dn[3], dm[3], dr;
-    texel_finish_grad<kWorkflow>(t[i], tg[i], rough[i], S.vx, S.vy, S.vz, da, dn, &dr, dm);
+    V da[3], dn[3], dm[3], dr, g_ndv;
+    texel_finish_grad<kWorkflow>(t[i], tg[i], rough[i], S.vx, S.vy, S.vz, da, dn, &dr, dm, kGeom ? &g_ndv : nullptr);
+    if (kGeom) {
+      g_view[i][0] += g_ndv * t[i].nx; g_view[i][1] += g_ndv * t[i].ny; g_view[i][2] += g_ndv * t[i].nz;
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       d_albedo[c][i] = da[c];
@@ -321,6 +350,14 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
       d_met[c][i] = dm[c];
     }
     d_rough[i] = dr;
+  }
+  if (kGeom) {
+    float gv[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gv[c] += lane_sum(g_view[i][c]);
+    geom_sink.view(gv);
   }
 }
 

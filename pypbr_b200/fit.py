@@ -9,7 +9,8 @@ d loss / d(albedo, normal, roughness, metallic | specular) - the rendered image 
 
 Multi-GPU: materials are independent, so the batch is sharded across ranks with no data-path
 collective; the only exchange is ONE all-reduce per step over a (1 + 3L)-float buffer holding the
-loss sum and the gradient of the shared light intensities (`allreduce_loss_and_shared`).
+loss sum and the gradients of the shared parameters - light intensities and, on request, light positions /
+directions and the view direction (`allreduce_loss_and_shared`).
 """
 
 from __future__ import annotations
@@ -45,6 +46,7 @@ def fused_loss_step(
     loss_scale: Optional[float] = None,
     want_intensity_grad: bool = False,
     out: Optional[Dict[str, torch.Tensor]] = None,
+    want_geometry_grad: bool = False,
 ):
     """
     One fused forward + MSE + backward pass over a (batched) material.
@@ -53,8 +55,10 @@ def fused_loss_step(
     loss_scale: factor applied to the gradients (default 1/target.numel(), i.e. nn.MSELoss()).
     out: optional dict of preallocated gradient / scratch buffers to reuse between steps
          (keys d_albedo, d_normal, d_roughness, d_metspec, buf).
-    Returns (buf, grads): buf is a device tensor [loss_sum, d_intensity(L*3)...] (loss_sum is the
-    UNscaled sum of squared errors; multiply by loss_scale for the mean), grads a dict of tensors.
+    want_geometry_grad: also the gradients of the light positions / directions and of the view direction (shared
+         parameters of a fit with unknown lighting); buf then has 1 + 6L + 3 floats.
+    Returns (buf, grads): buf is a device tensor [loss_sum, d_intensity(L*3)..., (d_lights(L*3)..., d_view(3))]
+    (loss_sum is the UNscaled sum of squared errors; multiply by loss_scale for the mean), grads a dict of tensors.
     """
     lib = _cabi.load()
     cfg, (albedo, normal, roughness, metspec), _leaf, device = _prepare(
@@ -86,11 +90,15 @@ def fused_loss_step(
     g.d_albedo, g.d_normal = _cabi.plane(d_albedo), _cabi.plane(d_normal)
     g.d_roughness, g.d_metspec = _cabi.plane(d_rough), _cabi.plane(d_met)
     red = out.get("buf")
-    if red is None or red.numel() != 1 + 3 * cfg.L:
-        red = torch.empty(1 + 3 * cfg.L, dtype=torch.float32, device=device)
+    n_red = 1 + 3 * cfg.L + ((3 * cfg.L + 3) if want_geometry_grad else 0)
+    if red is None or red.numel() != n_red:
+        red = torch.empty(n_red, dtype=torch.float32, device=device)
         out["buf"] = red
     red.zero_()
     g.d_intensity = red[1:].data_ptr() if want_intensity_grad else None
+    if want_geometry_grad:
+        g.d_lights = red[1 + 3 * cfg.L:].data_ptr()
+        g.d_view = red[1 + 6 * cfg.L:].data_ptr()
     ls = _cabi.PbrCtLoss()
     ls.target, ls.target_sl = _out_plane(target, cfg.per_light, cfg.batched)
     ls.loss_scale = float(loss_scale)

@@ -104,7 +104,7 @@ def _out_shape(cfg: _ShadeCfg, albedo: Tensor):
 
 class _CookTorranceFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, cfg: _ShadeCfg, albedo, normal, roughness, metspec, intensity_leaf):
+    def forward(ctx, cfg: _ShadeCfg, albedo, normal, roughness, metspec, intensity_leaf, lights_leaf=None, view_leaf=None):
         lib = _cabi.load()
         keep: list = []
         d = _fill_desc(cfg, albedo, normal, roughness, metspec, keep)
@@ -114,6 +114,8 @@ class _CookTorranceFn(torch.autograd.Function):
             _cabi.check(lib.pbr_ct_forward(_cabi.byref(d), _cabi.stream_ptr(albedo.device)), "pbr_ct_forward")
         ctx.cfg = cfg
         ctx.has_normal = normal is not None
+        # the shared parameters may live on another device than the maps (the reference moves them with .to(device))
+        ctx.leaf_meta = [(t.device, tuple(t.shape)) if t is not None else None for t in (intensity_leaf, lights_leaf, view_leaf)]
         ctx.save_for_backward(albedo, normal if normal is not None else albedo.new_empty(0), roughness, metspec)
         return out
 
@@ -129,7 +131,7 @@ class _CookTorranceFn(torch.autograd.Function):
         grad_out = grad_out.contiguous()
         g = _cabi.PbrCtGrads()
         g.grad_out, g.grad_out_sl = _out_plane(grad_out, cfg.per_light, cfg.batched)
-        need = ctx.needs_input_grad  # (cfg, albedo, normal, roughness, metspec, intensity)
+        need = ctx.needs_input_grad  # (cfg, albedo, normal, roughness, metspec, intensity, lights, view)
         dev = albedo.device
         d_albedo = torch.empty(albedo.shape, dtype=torch.float32, device=dev) if need[1] else None
         d_normal = torch.empty(normal.shape, dtype=torch.float32, device=dev) if (need[2] and normal is not None) else None
@@ -141,14 +143,23 @@ class _CookTorranceFn(torch.autograd.Function):
         g.d_roughness = _cabi.plane(d_rough)
         g.d_metspec = _cabi.plane(d_met)
         g.d_intensity = d_int.data_ptr() if d_int is not None else None
+        # gradients of the light positions / directions and of the view direction (plain autograd in the reference)
+        d_lights = torch.zeros(cfg.L, 3, dtype=torch.float32, device=dev) if need[6] else None
+        d_view = torch.zeros(3, dtype=torch.float32, device=dev) if need[7] else None
+        g.d_lights = d_lights.data_ptr() if d_lights is not None else None
+        g.d_view = d_view.data_ptr() if d_view is not None else None
         with torch.cuda.device(dev):
             _cabi.check(lib.pbr_ct_backward(_cabi.byref(d), _cabi.byref(g), _cabi.stream_ptr(dev)), "pbr_ct_backward")
-        return None, d_albedo, d_normal, d_rough, d_met, d_int
+        shared = []
+        for t, meta in zip((d_int, d_lights, d_view), ctx.leaf_meta):
+            shared.append(t.reshape(meta[1]).to(meta[0]) if (t is not None and meta is not None) else None)
+        return (None, d_albedo, d_normal, d_rough, d_met, *shared)
 
 
 def _prepare(material: MaterialBase, device, view_dir, light, intensity, light_type: str, light_size, return_srgb: bool,
              multi_light: str):
-    """Host-side validation in the reference's order (cooktorrance.py:92-118); returns (cfg, maps, intensity leaf)."""
+    """Host-side validation in the reference's order (cooktorrance.py:92-118); returns (cfg, maps, shared-parameter
+    leaves (intensity, lights, view - None where no gradient is wanted), device)."""
     # attribute / workflow errors first, exactly where the reference raises them (cooktorrance.py:99-118)
     roughness = material.roughness  # AttributeError if the map was never set
     normal = material.normal  # AttributeError unless the key exists (None selects the +Z default)
@@ -227,13 +238,13 @@ def _prepare(material: MaterialBase, device, view_dir, light, intensity, light_t
     if cfg.L > _cabi.PBR_MAX_LIGHTS:
         raise ValueError(f"at most {_cabi.PBR_MAX_LIGHTS} lights per call, got {cfg.L}")
     cfg.per_light = cfg.multi and multi_light == "per_light"
-    for t, nm in ((view, "view_dir"), (lights, "light_dir_or_position")):
-        if t.requires_grad:
-            raise NotImplementedError(f"pypbr_b200: gradients w.r.t. {nm} are not implemented (intensity and maps are).")
     if view.numel() != 3:
         raise ValueError(f"view_dir must have shape (3,), got {tuple(view.shape)}")
 
-    intensity_leaf = inten if inten.requires_grad else None
+    # views of the caller's tensors: their (L, 3) / (3,) gradients reach the caller through autograd's view tracking
+    shared_leaves = (inten if inten.requires_grad else None,
+                     lights if lights.requires_grad else None,
+                     view if view.requires_grad else None)
     all_dev = all(t.is_cuda and t.device == device for t in (view, lights, inten))
     cfg.on_device = all_dev
     if all_dev:
@@ -244,7 +255,7 @@ def _prepare(material: MaterialBase, device, view_dir, light, intensity, light_t
         cfg.view = view.detach().reshape(3).to(torch.float32).cpu().tolist()
         cfg.lights = lights.detach().to(torch.float32).cpu().reshape(-1).tolist()
         cfg.intensity = inten.detach().to(torch.float32).cpu().reshape(-1).tolist()
-    return cfg, (albedo, normal, roughness, metspec), intensity_leaf, device
+    return cfg, (albedo, normal, roughness, metspec), shared_leaves, device
 
 
 class CookTorranceBRDF(BRDFModel):
@@ -282,10 +293,10 @@ class CookTorranceBRDF(BRDFModel):
             Tensor (3, H, W); (B, 3, H, W) for batched maps; (..., L, 3, H, W) in per_light mode.
         """
         device = self.override_device or material.device
-        cfg, (albedo, normal, roughness, metspec), intensity_leaf, _ = _prepare(
+        cfg, (albedo, normal, roughness, metspec), shared_leaves, _ = _prepare(
             material, device, view_dir, light_dir_or_position, light_intensity, self.light_type, light_size,
             return_srgb, self.multi_light,
         )
-        # `intensity_leaf` is a view of the caller's tensor, so its (L, 3) gradient reaches the caller's
-        # (3,) or (L, 3) tensor through autograd's view tracking.
-        return _CookTorranceFn.apply(cfg, albedo, normal, roughness, metspec, intensity_leaf)
+        # the shared-parameter leaves are views of the caller's tensors, so e.g. the (L, 3) intensity gradient reaches
+        # the caller's (3,) or (L, 3) tensor through autograd's view tracking.
+        return _CookTorranceFn.apply(cfg, albedo, normal, roughness, metspec, *shared_leaves)

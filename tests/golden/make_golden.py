@@ -334,10 +334,49 @@ def make_config1_fixture():
     print(f"config1_tiles_256: ok  mean {out.mean():.7f} min {out.min():.5f} max {out.max():.5f}")
 
 
+def make_geomgrad_cases():
+    """Gradients of the shared geometry parameters (view_dir, light position / direction) and of the intensity, from
+    the reference's own autograd (cooktorrance.py:95,125-140), fp32 and fp64; the oracle must agree bit for bit."""
+    arrs = {}
+    cases = [dict(tag="point_metal", workflow="metallic", light_type="point", light_size=1.0, H=24, W=36,
+                  view=[0.15, -0.1, 0.9], light=[0.3, 0.2, 0.8], intensity=[1.2, 1.0, 0.8]),
+             dict(tag="dir_spec", workflow="specular", light_type="directional", light_size=None, H=20, W=28,
+                  view=[-0.2, 0.1, 1.0], light=[0.3, -0.2, 0.9], intensity=[2.0, 1.5, 1.0])]
+    for ci, c in enumerate(cases):
+        gen = torch.Generator().manual_seed(4000 + ci)
+        maps = synth_maps(gen, c["H"], c["W"], c["workflow"])
+        grad_out = torch.rand(3, c["H"], c["W"], generator=gen)
+        p = dict(light_type=c["light_type"], light_size=c["light_size"], return_srgb=True, albedo_is_srgb=True,
+                 specular_is_srgb=True, accumulate=True)
+        for dtype, tag in ((torch.float32, "32"), (torch.float64, "64")):
+            shared = [torch.tensor(c[k], dtype=dtype, requires_grad=True) for k in ("view", "light", "intensity")]
+            mat, _ = ref_material(maps, dtype, p)
+            out = CookTorranceBRDF(light_type=c["light_type"])(mat, shared[0], shared[1], shared[2], c["light_size"], True)
+            out.backward(grad_out.to(dtype))
+            oshared = [torch.tensor(c[k], dtype=dtype, requires_grad=True) for k in ("view", "light", "intensity")]
+            oout = O.render({k: t.to(dtype) for k, t in maps.items()}, oshared[0], oshared[1], oshared[2], c["light_size"],
+                            c["light_type"], True, True, True, True)
+            oout.backward(grad_out.to(dtype))
+            assert bits_equal(oout, out), f"geomgrad {c['tag']}: oracle forward differs ({tag})"
+            for a, b, nm in zip(shared, oshared, ("view", "light", "intensity")):
+                assert bits_equal(a.grad, b.grad), f"geomgrad {c['tag']}: oracle d_{nm} differs ({tag})"
+                arrs[f"{c['tag']}_g{tag}_{nm}"] = a.grad.numpy()
+        for k, v in maps.items():
+            arrs[f"{c['tag']}_in_{k}"] = v.numpy()
+        arrs[f"{c['tag']}_grad_out"] = grad_out.numpy()
+        arrs[f"{c['tag']}_params"] = np.array(json.dumps({**p, **{k: c[k] for k in ("view", "light", "intensity", "workflow")}}))
+        print(f"geomgrad {c['tag']}: ok  d_view64 {arrs[c['tag'] + '_g64_view']}  d_light64 {arrs[c['tag'] + '_g64_light']}")
+    np.savez_compressed(os.path.join(HERE, "geomgrad_shared_params.npz"), **arrs)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "geomgrad":   # only this fixture (the others are unchanged)
+        make_geomgrad_cases()
+        sys.exit(0)
     for i, c in enumerate(CT_CASES):
         make_ct_case(i, c)
     make_conversion_cases()
     make_blend_cases()
     make_config1_fixture()
+    make_geomgrad_cases()

@@ -17,6 +17,15 @@ struct Dims {
   int B, H, W, L;
 };
 
+// sums in double: [L][3] w.r.t. light position / unit direction, then [3] w.r.t. the unit view direction
+struct HostGeomSink {
+  static constexpr bool kOn = true;
+  double* d_geo;
+  int L;
+  void light(int l, const float (&g)[3]) const { for (int c = 0; c < 3; ++c) d_geo[3 * l + c] += g[c]; }
+  void view(const float (&g)[3]) const { for (int c = 0; c < 3; ++c) d_geo[3 * L + c] += g[c]; }
+};
+
 // kLightPointCached: what the kernels' prologue does per texel pair, with a private cache
 template <int LIGHT, class V>
 GeomCache<V> fill_cache(const CtStage& S, int L, V x, float y, V* store) {
@@ -72,7 +81,7 @@ template <int WF, bool HASN, int LIGHT, class V>
 void bwd_impl(const Dims& d, const CtStage& S, const CtFlags& F, const float* albedo, const float* normal,
               const float* rough, const float* metspec, const float* grad_out, const float* target,
               float loss_scale, double* loss_sum, float* d_albedo, float* d_normal, float* d_rough, float* d_met,
-              double* d_int) {
+              double* d_int, double* d_geo = nullptr) {
   constexpr int NL = Lanes<V>::n;
   const int mc = WF == 0 ? 1 : 3;  // WF 2: metallic with 3 channels
   const int64_t HW = (int64_t)d.H * d.W;
@@ -117,8 +126,17 @@ void bwd_impl(const Dims& d, const CtStage& S, const CtFlags& F, const float* al
         if (LIGHT == kLightPointHoisted)
           point_light_geom(S.light[0].p[0], S.light[0].p[1], S.light[0].p[2], x[0], y, S.vx, S.vy, S.vz, hg[0]);
         V store[PBR_MAX_LIGHTS * 8];
-        ct_backward_group<WF, LIGHT, V, 1>(S, F, a, n, r, m, x, y, hg, gout, sink, da, dn, dr, dm, NoFetch(),
-                                           fill_cache<LIGHT, V>(S, d.L, x[0], y, store));
+        bool done = false;
+        if constexpr (LIGHT == kLightDirectional || LIGHT == kLightPoint) {
+          if (d_geo) {   // gradients of the light positions / directions and of the view direction
+            ct_backward_group<WF, LIGHT, V, 1>(S, F, a, n, r, m, x, y, hg, gout, sink, da, dn, dr, dm, NoFetch(),
+                                               GeomCache<V>(), HostGeomSink{d_geo, d.L});
+            done = true;
+          }
+        }
+        if (!done)
+          ct_backward_group<WF, LIGHT, V, 1>(S, F, a, n, r, m, x, y, hg, gout, sink, da, dn, dr, dm, NoFetch(),
+                                             fill_cache<LIGHT, V>(S, d.L, x[0], y, store));
         for (int k = 0; k < live; ++k) {
           for (int c = 0; c < 3; ++c) d_albedo[(b * 3 + c) * HW + o[k]] = lane_get(da[c][0], k);
           if (HASN && d_normal)
@@ -198,6 +216,34 @@ int hs_ct_backward(int B, int H, int W, int L, int workflow, int light_type, int
   CtFlags F{L, light_type == 1, albedo_is_srgb != 0, specular_is_srgb != 0, return_srgb != 0, per_light != 0};
   DISPATCH(bwd_impl, d, S, F, albedo, normal, rough, metspec, grad_out, target, loss_scale, loss_sum, d_albedo,
            d_normal, d_rough, d_met, d_int);
+  return 0;
+}
+
+// As hs_ct_backward, plus d_lights (L*3) and d_view (3): gradients w.r.t. the light positions / raw directions and the raw
+// view direction.  Always the uncached per-texel light modes (what the kernels pick when these are requested).
+int hs_ct_backward_geom(int B, int H, int W, int L, int workflow, int light_type, int albedo_is_srgb, int specular_is_srgb,
+                        int return_srgb, int per_light, float light_size, const float* albedo, const float* normal,
+                        const float* rough, const float* metspec, const float* view, const float* lights,
+                        const float* inten, const float* grad_out, const float* target, float loss_scale,
+                        double* loss_sum, float* d_albedo, float* d_normal, float* d_rough, float* d_met, double* d_int,
+                        double* d_lights, double* d_view, int force_generic) {
+  if (L > PBR_MAX_LIGHTS) return -4;
+  Dims d{B, H, W, L};
+  static CtStage S;
+  make_stage(d, light_type, light_size, view, lights, inten, S);
+  CtFlags F{L, light_type == 1, albedo_is_srgb != 0, specular_is_srgb != 0, return_srgb != 0, per_light != 0};
+  std::vector<double> geo(3 * L + 3, 0.0);
+  force_generic = (force_generic & 2) | 1;
+  DISPATCH(bwd_impl, d, S, F, albedo, normal, rough, metspec, grad_out, target, loss_scale, loss_sum, d_albedo,
+           d_normal, d_rough, d_met, d_int, geo.data());
+  for (int l = 0; l <= L; ++l) {
+    const float g[3] = {(float)geo[3 * l], (float)geo[3 * l + 1], (float)geo[3 * l + 2]};
+    float o[3] = {g[0], g[1], g[2]};
+    if (l == L) normalize_bwd(view, g, o);
+    else if (light_type != 1) normalize_bwd(lights + 3 * l, g, o);
+    double* dst = l == L ? d_view : d_lights + 3 * l;
+    for (int c = 0; c < 3; ++c) dst[c] = o[c];
+  }
   return 0;
 }
 

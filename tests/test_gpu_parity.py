@@ -654,3 +654,90 @@ def test_fit_step_rejects_what_the_one_launch_path_cannot_update_in_place():
     other = {k: v.clone() for k, v in leaves.items()}
     with pytest.raises(ValueError):   # not the material's own tensors
         fused_fit_step(mat, FusedAdam(other), target, view, lights, inten)
+
+
+def _shared_tol(want):
+    want = np.asarray(want, np.float64)
+    return 1e-4 * np.abs(want) + 1e-4 * np.abs(want).mean()
+
+
+@pytest.mark.parametrize("tag", ["point_metal", "dir_spec"])
+def test_light_and_view_gradients_match_reference_fixture(tag):
+    """view_dir / light position | direction / intensity gradients through autograd of the public API against the
+    REFERENCE's own autograd results (tests/golden/geomgrad_shared_params.npz, fp64 run as the arbiter: these are sums
+    over the whole image)."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    z = np.load(os.path.join(GOLDEN, "geomgrad_shared_params.npz"))
+    p = json.loads(str(z[tag + "_params"]))
+    names = ("albedo", "normal", "roughness", "metallic" if p["workflow"] == "metallic" else "specular")
+    mat, _ = _material({k: z[f"{tag}_in_{k}"] for k in names}, p)
+    for where in ("cpu", "cuda"):   # CPU leaves (the reference's usual call) and device-resident parameters
+        view, light, inten = (torch.tensor(p[k], device=where, requires_grad=True) for k in ("view", "light", "intensity"))
+        out = _brdf(p, False)(mat, view, light, inten, p["light_size"], True)
+        out.backward(torch.from_numpy(z[tag + "_grad_out"]).to(DEV))
+        for t, key in ((view, "view"), (light, "light"), (inten, "intensity")):
+            assert t.grad is not None and t.grad.device.type == where and t.grad.shape == t.shape
+            want = z[f"{tag}_g64_{key}"]
+            assert np.all(np.abs(t.grad.cpu().numpy() - want) <= _shared_tol(want)), (key, t.grad, want)
+
+
+@pytest.mark.parametrize("light_type,B,L,per_light,wf", [("point", 3, 4, False, "metallic"), ("point", 2, 3, True, "specular"),
+                                                         ("directional", 2, 3, False, "metallic"), ("point", None, 1, False, "metallic")])
+def test_light_and_view_gradients_against_oracle(light_type, B, L, per_light, wf):
+    """Batched / multi-light: the gradients of the shared parameters are sums over materials (and lights, for the
+    view) of the reference's single-call gradients; map gradients must not change when they are requested."""
+    from oracle import pbr_oracle as O
+
+    maps, lights, inten, g = _random_case(300 + L, B, 26, 38, L, workflow=wf)
+    if L == 1:
+        lights, inten = lights.view(3), inten.view(3)
+    view = torch.tensor([0.12, -0.08, 0.95])
+    p = dict(light_type=light_type)
+    size = 1.0 if light_type == "point" else None
+    v64, l64, i64 = (t.double().clone().requires_grad_(True) for t in (view, lights, inten))
+    ref = O.render({k: t.double() for k, t in maps.items()}, v64, l64, i64, size, light_type, accumulate=not per_light)
+    go = torch.rand(ref.shape, generator=g)
+    ref.backward(go.double())
+
+    mat, leaves = _material(maps, p, requires_grad=True)
+    vd, ld, idv = (t.clone().requires_grad_(True) for t in (view, lights, inten))
+    out = _brdf(p, per_light)(mat, vd, ld, idv, size, True)
+    out.backward(go.to(DEV))
+    for t, want, key in ((vd, v64.grad, "view"), (ld, l64.grad, "lights"), (idv, i64.grad, "intensity")):
+        want = want.numpy()
+        assert np.all(np.abs(t.grad.numpy() - want) <= _shared_tol(want)), (key, t.grad, want)
+    # same map gradients as the kernels that do not compute the shared-parameter gradients
+    mat2, leaves2 = _material(maps, p, requires_grad=True)
+    _brdf(p, per_light)(mat2, view, lights, inten, size, True).backward(go.to(DEV))
+    for k in leaves:
+        a, b = leaves[k].grad, leaves2[k].grad
+        assert bool(((a - b).abs() <= 2e-6 * b.abs() + 2e-6 * b.abs().mean()).all()), k
+
+
+def test_fused_loss_step_delivers_shared_parameter_gradients():
+    """[loss, d_intensity, d_lights, d_view]: the 1 + 6L + 3 float buffer a sharded fit all-reduces."""
+    from oracle import pbr_oracle as O
+    from pypbr_b200.fit import fused_loss_step
+
+    L = 3
+    maps, lights, inten, g = _random_case(55, 2, 20, 32, L)
+    view = torch.tensor([0.05, 0.1, 1.0])
+    v64, l64, i64 = (t.double().clone().requires_grad_(True) for t in (view, lights, inten))
+    ref = O.render({k: t.double() for k, t in maps.items()}, v64, l64, i64, 1.0, "point", accumulate=False)
+    target = torch.rand(ref.shape, generator=g)
+    loss = ((ref - target.double()) ** 2).mean()
+    loss.backward()
+    mat, _ = _material(maps, dict(light_type="point"))
+    buf, _grads = fused_loss_step(mat, target.to(DEV), view, lights, inten, "point", 1.0, want_intensity_grad=True,
+                                  want_geometry_grad=True)
+    buf = buf.cpu().numpy().astype(np.float64)
+    assert buf.shape == (1 + 6 * L + 3,)
+    assert abs(buf[0] / target.numel() - float(loss)) <= 1e-5 * float(loss)
+    for got, want, key in ((buf[1:1 + 3 * L], i64.grad, "intensity"), (buf[1 + 3 * L:1 + 6 * L], l64.grad, "lights"),
+                           (buf[1 + 6 * L:], v64.grad, "view")):
+        want = want.numpy().reshape(-1)
+        assert np.all(np.abs(got - want) <= _shared_tol(want)), (key, got, want)

@@ -224,3 +224,74 @@ def test_shared_reciprocal_division_is_ieee(hostsim):
     a = (rng.standard_normal(n) * np.exp(rng.uniform(-6, 6, n))).astype(np.float32)
     b = np.exp(rng.uniform(-8, 8, n)).astype(np.float32)
     assert hostsim.hs_div_check(ctypes.c_int64(n), fp(a), fp(b)) == 0
+
+
+@pytest.mark.parametrize("light_type,L,per_light,packed", [("point", 1, False, 0), ("point", 3, True, 2), ("point", 4, False, 2),
+                                                           ("directional", 1, False, 2), ("directional", 3, False, 0)])
+def test_light_and_view_gradients_against_oracle(hostsim, light_type, L, per_light, packed):
+    """d/d(light position | direction) and d/d(view direction), which the reference gets from plain autograd
+    (cooktorrance.py:95,125-140), against autograd through the oracle in fp64 (sums over the image: the fp32 oracle's
+    own summation noise is larger than the kernel's error)."""
+    from oracle import pbr_oracle as O
+
+    gen = torch.Generator().manual_seed(31 + L)
+    B, H, W = 2, 21, 30
+    maps = {"albedo": torch.rand(B, 3, H, W, generator=gen), "roughness": torch.rand(B, 1, H, W, generator=gen) * 0.8 + 0.2,
+            "metallic": torch.rand(B, 1, H, W, generator=gen)}
+    n = torch.randn(B, 3, H, W, generator=gen) * torch.tensor([0.3, 0.3, 0.0]).view(1, 3, 1, 1) + torch.tensor([0.0, 0.0, 1.0]).view(1, 3, 1, 1)
+    maps["normal"] = torch.nn.functional.normalize(n, dim=1)
+    ang = torch.arange(L, dtype=torch.float32) * (6.2831853 / L) + 0.3
+    lights = torch.stack([0.4 * torch.cos(ang), 0.4 * torch.sin(ang), torch.ones(L) * 0.8], dim=1)
+    inten = torch.rand(L, 3, generator=gen) * (1.0 if per_light else 1.5 / L) + 0.2
+    view = torch.tensor([0.15, -0.1, 0.9])
+    size = 1.0 if light_type == "point" else None
+
+    v64, l64, i64 = (t.double().clone().requires_grad_(True) for t in (view, lights, inten))
+    out = O.render({k: t.double() for k, t in maps.items()}, v64, l64, i64, size, light_type, accumulate=not per_light)
+    go = torch.rand(out.shape, generator=gen)
+    out.backward(go.double())
+
+    a = {k: np.ascontiguousarray(t.numpy()) for k, t in maps.items()}
+    vn, ln, inn, gon = (np.ascontiguousarray(t.numpy()) for t in (view, lights, inten, go))
+    args = (B, H, W, L, 0, 1 if light_type == "point" else 0, 1, 1, 1, int(per_light), ctypes.c_float(size or 0.0),
+            fp(a["albedo"]), fp(a["normal"]), fp(a["roughness"]), fp(a["metallic"]), fp(vn), fp(ln), fp(inn))
+    da = np.zeros_like(a["albedo"]); dn = np.zeros_like(a["albedo"]); dr = np.zeros_like(a["roughness"]); dm = np.zeros_like(a["metallic"])
+    di = np.zeros((L, 3), np.float64); dl = np.zeros((L, 3), np.float64); dv = np.zeros(3, np.float64)
+    loss = ctypes.c_double(0)
+    rc = hostsim.hs_ct_backward_geom(*args, fp(gon), None, ctypes.c_float(0), ctypes.byref(loss), fp(da), fp(dn), fp(dr), fp(dm),
+                                     di.ctypes.data_as(D), dl.ctypes.data_as(D), dv.ctypes.data_as(D), packed)
+    assert rc == 0
+    for name, got, want in (("d_lights", dl, l64.grad.numpy()), ("d_view", dv, v64.grad.numpy()), ("d_intensity", di, i64.grad.numpy())):
+        tol = 1e-4 * np.abs(want) + 1e-4 * np.abs(want).mean()
+        assert np.all(np.abs(got - want) <= tol), (name, got, want)
+
+
+@pytest.mark.parametrize("tag", ["point_metal", "dir_spec"])
+def test_light_and_view_gradients_match_reference_fixture(hostsim, tag):
+    """geomgrad_shared_params.npz holds the REFERENCE's own autograd gradients of view_dir, the light position /
+    direction and the intensity (make_golden.py geomgrad)."""
+    import json
+
+    z = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "geomgrad_shared_params.npz"))
+    p = json.loads(str(z[tag + "_params"]))
+    wf = 0 if p["workflow"] == "metallic" else 1
+    a = {k: np.ascontiguousarray(z[f"{tag}_in_{k}"]) for k in ("albedo", "normal", "roughness", "metallic" if wf == 0 else "specular")}
+    ms = a["metallic" if wf == 0 else "specular"]
+    H, W = a["albedo"].shape[-2:]
+    vn, ln, inn = (np.asarray(p[k], np.float32) for k in ("view", "light", "intensity"))
+    go = np.ascontiguousarray(z[tag + "_grad_out"])
+    args = (1, H, W, 1, wf, 1 if p["light_type"] == "point" else 0, 1, 1, 1, 0, ctypes.c_float(p["light_size"] or 0.0),
+            fp(a["albedo"]), fp(a["normal"]), fp(a["roughness"]), fp(ms), fp(vn), fp(ln), fp(inn))
+    da = np.zeros_like(a["albedo"]); dn = np.zeros_like(a["albedo"]); dr = np.zeros_like(a["roughness"]); dm = np.zeros_like(ms)
+    di = np.zeros((1, 3), np.float64); dl = np.zeros((1, 3), np.float64); dv = np.zeros(3, np.float64)
+    loss = ctypes.c_double(0)
+    for packed in (0, 2):
+        dl[:] = 0; dv[:] = 0; di[:] = 0
+        assert hostsim.hs_ct_backward_geom(*args, fp(go), None, ctypes.c_float(0), ctypes.byref(loss), fp(da), fp(dn), fp(dr),
+                                           fp(dm), di.ctypes.data_as(D), dl.ctypes.data_as(D), dv.ctypes.data_as(D), packed) == 0
+        for name, got, key in (("d_light", dl[0], "light"), ("d_view", dv, "view"), ("d_intensity", di[0], "intensity")):
+            want = z[f"{tag}_g64_{key}"]
+            tol = 1e-4 * np.abs(want) + 1e-4 * np.abs(want).mean()
+            assert np.all(np.abs(got - want) <= tol), (name, got, want)
+            # the reference's own fp32 run is further from fp64 than that or in the same ballpark
+            assert np.all(np.abs(got - want) <= 4 * np.abs(z[f"{tag}_g32_{key}"] - want) + tol)
