@@ -136,6 +136,18 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
   return p - d.step_size * xdiv(m, denom);
 }
 
+// The same update for the epilogue of the fused fit step, on lane-values (packed FP32) and with the MUFU reciprocal /
+// reciprocal square root (relative error ~2e-7 on a step that is lr-sized): the IEEE division and square root of
+// adam_update cost ~50 instructions per element, a quarter of the whole fit kernel at 8 lights.
+template <class VV>
+__device__ __forceinline__ VV adam_update_fast(VV p, VV g, VV& m, VV& v, const AdamCoef& d, float inv_bias2_sqrt) {
+  m = m + (g - m) * d.one_minus_beta1;
+  v = v * d.beta2 + (g * g) * d.one_minus_beta2;
+  const VV sv = v * seed_rsqrt(vmax(v, 1e-36f));   // sqrt(v); 0 for v == 0
+  const VV denom = sv * inv_bias2_sqrt + d.eps;
+  return p - (m * d.step_size) * fast_rcp(denom);
+}
+
 struct CtKParams {
   int B, H, W;
   int mats_per_cta;      // materials a thread walks over (blockIdx.z selects the chunk)
@@ -157,6 +169,7 @@ struct CtKParams {
   // fused fit step (pbr_ct_fit_step): the epilogue applies Adam + projection to the maps in place instead of
   // writing the gradients.  Moments in the order albedo, normal, roughness, metspec.
   int adam_on, adam_project;
+  int adam_smem_off;     // byte offset of the Adam staging area in the dynamic shared memory (after the geometry cache)
   AdamCoef adam;
   PbrPlane adam_m[4], adam_v[4];
   // staging sources
@@ -401,6 +414,8 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
   LightGeomT<V> hg[kSlots];
   GeomCache<V> gc;
   grid_coords<kLight>(S, w, p.flags.L, x, y, hg, gc);
+  // Adam staging of the fused fit step: [channel slot][p | m | v][thread][texel], this thread's column
+  float* const s_adam = reinterpret_cast<float*>(s_dyn + p.adam_smem_off) + tid * kCtTexels;
 
   float loss_local = 0.0f;
   const int b0 = blockIdx.z * p.mats_per_cta;
@@ -408,6 +423,41 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
   for (int b = b0; b < b1; ++b) {
     float araw[3][kCtTexels], nraw[3][kCtTexels], rough[kCtTexels], mraw[3][kCtTexels];
     load_material<WF>(p, w, b, araw, nraw, rough, mraw);
+    if (p.adam_on) {
+      // Fused fit step: what the Adam epilogue of THIS material needs (parameters and both moments of every channel)
+      // starts travelling now, as per-thread cp.async copies into shared memory, and lands while the light loop runs.
+      // A dependent load -> update -> store chain per channel in the epilogue would expose 8 DRAM round trips per
+      // material (measured: 25.1 instead of 13.3 + 4.6 ms on C5).  The group is older than the target ring's groups,
+      // so the ring's first wait also covers it.
+      int ch = 0;
+      auto send = [&](const PbrPlane& P, int q, int c) {
+        const float* src[3] = {P.ptr + plane_off(P, b, c, w.row, w.col0), p.adam_m[q].ptr + plane_off(p.adam_m[q], b, c, w.row, w.col0),
+                               p.adam_v[q].ptr + plane_off(p.adam_v[q], b, c, w.row, w.col0)};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float* dst = s_adam + ((3 * ch + j) * kCtThreads) * kCtTexels;
+          if (kCtTexels == 2 && w.vec) {
+            cp_async8(dst, src[j]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < kCtTexels; ++i) cp_async4(dst + i, src[j] + (i < w.valid ? i : (w.valid > 0 ? w.valid - 1 : 0)));
+          }
+        }
+        ++ch;
+      };
+#pragma unroll
+      for (int c = 0; c < 3; ++c) send(p.albedo, 0, c);
+      if (p.normal.ptr) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) send(p.normal, 1, c);
+      } else {
+        ch += 3;
+      }
+      send(p.roughness, 2, 0);
+#pragma unroll
+      for (int c = 0; c < (WF == 0 ? 1 : 3); ++c) send(p.metspec, 3, c);
+      cp_async_commit();
+    }
     float d_albedo[3][kCtTexels], d_normal[3][kCtTexels], d_rough[kCtTexels], d_met[3][kCtTexels];
 #pragma unroll
     for (int s = 0; s < kSlots; s += G) {
@@ -498,21 +548,29 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       for (int c = 0; c < 3; ++c) { unpair_to<G>(da[c], s, d_albedo[c]); unpair_to<G>(dn[c], s, d_normal[c]); unpair_to<G>(dm[c], s, d_met[c]); }
       unpair_to<G>(dr, s, d_rough);
     }
+    if (!w.active && p.adam_on) cp_async_wait<0>();
     if (w.active && p.adam_on) {
-      // fused fit step: the gradients never reach HBM.  Re-read the parameters (L2 / HBM: 32 B per texel in a kernel
-      // that is FP32-pipe bound) rather than keeping 16 registers alive across the light loop.
+      // fused fit step: the gradients never reach HBM; parameters and moments were prefetched into shared memory
       constexpr int mc = WF == 0 ? 1 : 3;
       const bool proj = p.adam_project != 0;
-      auto channel = [&](const PbrPlane& P, int q, int c, const float(&g)[kCtTexels], float(&pn)[kCtTexels]) {
+      cp_async_wait<0>();
+      int ch = 0;   // same channel order as the prefetch above
+      const float inv_b2 = 1.0f / p.adam.bias2_sqrt;
+      auto channel = [&](const PbrPlane&, int q, int c, const float(&g)[kCtTexels], float(&pn)[kCtTexels]) {
         float pv[kCtTexels], m[kCtTexels], v[kCtTexels];
-        const int64_t om = plane_off(p.adam_m[q], b, c, w.row, w.col0), ov = plane_off(p.adam_v[q], b, c, w.row, w.col0);
-        load_seg<kCtTexels>(P.ptr + plane_off(P, b, c, w.row, w.col0), w.vec, w.valid, pv);
-        load_seg<kCtTexels>(p.adam_m[q].ptr + om, w.vec, w.valid, m);
-        load_seg<kCtTexels>(p.adam_v[q].ptr + ov, w.vec, w.valid, v);
+        const float* st = s_adam + (3 * ch * kCtThreads) * kCtTexels;
 #pragma unroll
-        for (int i = 0; i < kCtTexels; ++i) pn[i] = adam_update(pv[i], g[i], m[i], v[i], p.adam);
-        store_seg<kCtTexels>(p.adam_m[q].ptr + om, w.vec, w.valid, m);
-        store_seg<kCtTexels>(p.adam_v[q].ptr + ov, w.vec, w.valid, v);
+        for (int i = 0; i < kCtTexels; ++i) {
+          pv[i] = st[i]; m[i] = st[kCtThreads * kCtTexels + i]; v[i] = st[2 * kCtThreads * kCtTexels + i];
+        }
+        ++ch;
+        V pp[kSlots], gp[kSlots], mp[kSlots], vp[kSlots];
+        pairs_of<kSlots>(pv, 0, pp); pairs_of<kSlots>(g, 0, gp); pairs_of<kSlots>(m, 0, mp); pairs_of<kSlots>(v, 0, vp);
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) pp[i] = adam_update_fast(pp[i], gp[i], mp[i], vp[i], p.adam, inv_b2);
+        unpair_to<kSlots>(pp, 0, pn); unpair_to<kSlots>(mp, 0, m); unpair_to<kSlots>(vp, 0, v);
+        store_seg<kCtTexels>(p.adam_m[q].ptr + plane_off(p.adam_m[q], b, c, w.row, w.col0), w.vec, w.valid, m);
+        store_seg<kCtTexels>(p.adam_v[q].ptr + plane_off(p.adam_v[q], b, c, w.row, w.col0), w.vec, w.valid, v);
       };
       auto put = [&](const PbrPlane& P, int c, float(&pn)[kCtTexels], bool clamp) {
         if (clamp) {
@@ -527,6 +585,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
         channel(p.albedo, 0, c, d_albedo[c], pn);
         put(p.albedo, c, pn, proj);
       }
+      if (!p.normal.ptr) ch += 3;
       if (p.normal.ptr) {
         float pn[3][kCtTexels];
 #pragma unroll
@@ -927,7 +986,7 @@ static void launch_dyn(const CtKParams& k, dim3 grid, dim3 block, size_t smem, c
   cudaGetDevice(&dev);
   const uint64_t bit = 1ull << (dev & 63);
   if (!(configured.load(std::memory_order_acquire) & bit)) {   // static + dynamic may exceed 48 KB before dynamic alone does
-    cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PBR_GC_MAX_BYTES);
+    cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PBR_GC_MAX_BYTES + 30 * kCtThreads * kCtTexels * 4);
     configured.fetch_or(bit, std::memory_order_release);
   }
   Kern<<<grid, block, smem, st>>>(k);
@@ -950,19 +1009,27 @@ static void launch_fwd(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t s
   }
 }
 
+// Adam staging of the fused fit step: parameter + two moments of up to 10 channels per texel (pbr_ct_fit_step)
+constexpr size_t kAdamSmemBytes = (size_t)30 * kCtThreads * kCtTexels * sizeof(float);
+
 template <int WF>
-static void launch_bwd(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t st) {
+static void launch_bwd(const CtKParams& k_in, dim3 grid, dim3 block, cudaStream_t st) {
+  CtKParams k = k_in;
+  const int lm = (k.d_lights || k.d_view) ? (k.flags.point ? kLightPoint : kLightDirectional) : light_mode(k);
+  const size_t cache = is_cached(lm) ? geom_cache_bytes(k.flags.L, lm) : 0;
+  k.adam_smem_off = (int)cache;
+  const size_t smem = cache + (k.adam_on ? kAdamSmemBytes : 0);
   if (k.d_lights || k.d_view) {   // geometry gradients: the uncached per-texel light modes
-    if (k.flags.point) ct_backward_kernel<WF, kLightPoint, true><<<grid, block, 0, st>>>(k);
-    else ct_backward_kernel<WF, kLightDirectional, true><<<grid, block, 0, st>>>(k);
+    if (k.flags.point) launch_dyn<ct_backward_kernel<WF, kLightPoint, true>>(k, grid, block, smem, st);
+    else launch_dyn<ct_backward_kernel<WF, kLightDirectional, true>>(k, grid, block, smem, st);
     return;
   }
-  switch (light_mode(k)) {
-    case kLightDirectional: ct_backward_kernel<WF, kLightDirectional><<<grid, block, 0, st>>>(k); break;
-    case kLightPoint: ct_backward_kernel<WF, kLightPoint><<<grid, block, 0, st>>>(k); break;
-    case kLightPointCached: launch_dyn<ct_backward_kernel<WF, kLightPointCached>>(k, grid, block, geom_cache_bytes(k.flags.L, kLightPointCached), st); break;
-    case kLightPointCachedAll: launch_dyn<ct_backward_kernel<WF, kLightPointCachedAll>>(k, grid, block, geom_cache_bytes(k.flags.L, kLightPointCachedAll), st); break;
-    default: ct_backward_kernel<WF, kLightPointHoisted><<<grid, block, 0, st>>>(k); break;
+  switch (lm) {
+    case kLightDirectional: launch_dyn<ct_backward_kernel<WF, kLightDirectional>>(k, grid, block, smem, st); break;
+    case kLightPoint: launch_dyn<ct_backward_kernel<WF, kLightPoint>>(k, grid, block, smem, st); break;
+    case kLightPointCached: launch_dyn<ct_backward_kernel<WF, kLightPointCached>>(k, grid, block, smem, st); break;
+    case kLightPointCachedAll: launch_dyn<ct_backward_kernel<WF, kLightPointCachedAll>>(k, grid, block, smem, st); break;
+    default: launch_dyn<ct_backward_kernel<WF, kLightPointHoisted>>(k, grid, block, smem, st); break;
   }
 }
 

@@ -594,8 +594,9 @@ def test_fused_adam_matches_torch_adam_and_fit_converges():
                                                  (6, "specular", True, True), (3, "metallic", False, False)])
 def test_one_launch_fit_step_equals_loss_kernel_plus_adam_kernel(L, wf, normal, project):
     """pbr_ct_fit_step (render + MSE + backward + Adam + projection in one launch, gradients in registers) must walk
-    the same trajectory as pbr_ct_loss_fwd_bwd followed by pbr_adam_step: same formulas on the same fp32 gradient
-    values (tolerance 2e-6 relative for multiply-add contraction differences between the two instantiations)."""
+    the same trajectory as pbr_ct_loss_fwd_bwd followed by pbr_adam_step: the same update on the same fp32 gradient
+    values; the epilogue evaluates it with the MUFU reciprocal / rsqrt (relative error ~2e-7 per step) and the two
+    instantiations contract multiply-adds differently, hence 4e-6 relative to |x| + mean|x| after four steps."""
     from pypbr_b200.fit import FusedAdam, fit_step
     from pypbr_b200.materials import BasecolorMetallicMaterial, DiffuseSpecularMaterial
     from pypbr_b200.models import CookTorranceBRDF
@@ -608,8 +609,9 @@ def test_one_launch_fit_step_equals_loss_kernel_plus_adam_kernel(L, wf, normal, 
     with torch.no_grad():
         target = CookTorranceBRDF("point", multi_light="per_light")(gt, view, lights, inten, 1.0)
     cls = BasecolorMetallicMaterial if wf == "metallic" else DiffuseSpecularMaterial
-    runs = []
-    for fused in (False, True):
+    from pypbr_b200.models import cooktorrance as ct
+
+    def make():
         pred = cls(albedo_is_srgb=True, device=DEV)
         leaves = {}
         for k, v in maps.items():
@@ -618,24 +620,38 @@ def test_one_launch_fit_step_equals_loss_kernel_plus_adam_kernel(L, wf, normal, 
             pred._maps[k] = leaves[k]
         if not normal:
             pred._maps["normal"] = None
-        opt = FusedAdam(leaves, lr=0.03, project=None if project else {k: None for k in leaves})
-        losses = []
+        return pred, leaves, FusedAdam(leaves, lr=0.03, project=None if project else {k: None for k in leaves})
+
+    (pa, la, oa), (pb, lb, ob) = make(), make()
+    losses = []
+    # the one-launch step always runs the generic kernels: pin the two-kernel step to them as well, so both see the
+    # same gradient code (streamed == generic is test_streamed_kernels_equal_generic_kernels' business)
+    ct.FORCE_GENERIC = True
+    try:
         for _ in range(4):
-            buf = fit_step(pred, opt, target, view, lights, inten, "point", 1.0, fused=fused)
-            losses.append(float(buf[0]))
-        runs.append((leaves, opt.state, losses))
-    (p0, s0, l0), (p1, s1, l1) = runs
-    assert l1[-1] < l1[0]
-    for a, b in zip(l0, l1):
-        assert abs(a - b) <= 1e-5 * abs(a)
-    for k in p0:
-        for a, b in ((p0[k], p1[k]), (s0[k][0], s1[k][0]), (s0[k][1], s1[k][1])):
-            err = (a - b).abs()
-            # an Adam step is lr-sized whatever the gradient: a one-ulp gradient difference near zero can flip a step,
-            # so allow a handful of outliers bounded by the step size
-            bad = err > 2e-6 * a.abs() + 1e-7
-            assert float(bad.float().mean()) < 1e-3, (k, float(err.max()))
-            assert float(err.max()) <= 0.07, (k, float(err.max()))
+            # same state before every step (an Adam step is lr-sized whatever the gradient, so two trajectories drift
+            # apart on noise-level gradients; what is compared here is ONE step from identical state)
+            for k in la:
+                lb[k].copy_(la[k]); ob.state[k][0].copy_(oa.state[k][0]); ob.state[k][1].copy_(oa.state[k][1])
+            ob.step_count = oa.step_count
+            buf_a = fit_step(pa, oa, target, view, lights, inten, "point", 1.0, fused=False)
+            buf_b = fit_step(pb, ob, target, view, lights, inten, "point", 1.0, fused=True)
+            losses.append(float(buf_a[0]))
+            assert abs(float(buf_a[0]) - float(buf_b[0])) <= 1e-6 * abs(float(buf_a[0]))
+            for k in la:
+                for a, b, what in ((la[k], lb[k], "param"), (oa.state[k][0], ob.state[k][0], "exp_avg"),
+                                   (oa.state[k][1], ob.state[k][1], "exp_avg_sq")):
+                    err = (a - b).abs()
+                    tol = 2e-6 * a.abs() + 1e-6 * a.abs().mean() + (2e-7 if what == "param" else 0.0)
+                    assert bool((err <= tol).all()), (k, what, float((err / tol).max()))
+    finally:
+        ct.FORCE_GENERIC = False
+    assert losses[-1] < losses[0]
+    if project:
+        assert float(lb["albedo"].min()) >= 0.0 and float(lb["albedo"].max()) <= 1.0
+        if normal:
+            nrm = lb["normal"].norm(dim=1)
+            assert torch.allclose(nrm, torch.ones_like(nrm), atol=1e-6)
 
 
 def test_fit_step_rejects_what_the_one_launch_path_cannot_update_in_place():
