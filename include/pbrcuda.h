@@ -239,6 +239,27 @@ typedef struct PbrAdamDesc {
 } PbrAdamDesc;
 
 /*
+ * Per-texel normal utilities of an augmentation pipeline.
+ *   ROTATE     : rotate_normals, pypbr/utils/functions.py:69-108 (the vector part of MaterialBase.rotate,
+ *                base.py:598-600): (x, y) @ R(angle)^T with cos_a / sin_a computed by the caller in double and
+ *                rounded to float as torch.tensor(...) does, then F.normalize over the 3 channels.  `in` has 3 channels;
+ *                in == out is allowed (the reference rotates in place).
+ *   FROM_HEIGHT: compute_normal_from_height, pypbr/utils/functions.py:123-177: grad_x = h[x-1] - h[x+1],
+ *                grad_y = h[y-1] - h[y+1] with zeros outside the image, normal = normalize(-gx*scale, -gy*scale, 1)
+ *                (flip_y = 0, OpenGL convention) or (-gx*scale, +gy*scale, 1) (flip_y = 1, DirectX).  `in` has 1 channel;
+ *                in and out must not overlap.
+ */
+enum { PBR_NORMAL_OP_ROTATE = 0, PBR_NORMAL_OP_FROM_HEIGHT = 1 };
+typedef struct PbrNormalOpDesc {
+  int32_t B, H, W;
+  int32_t op;               /* PBR_NORMAL_OP_* */
+  float cos_a, sin_a;       /* ROTATE */
+  float scale;              /* FROM_HEIGHT */
+  int32_t flip_y;           /* FROM_HEIGHT: 1 = NormalConvention.DIRECTX */
+  PbrPlane in, out;         /* out: 3 ch */
+} PbrNormalOpDesc;
+
+/*
  * Fused fit step ("Adam ... fused into K3's epilogue"): pbr_ct_loss_fwd_bwd whose epilogue
  * applies the Adam update + projection of pbr_adam_step to the maps IN PLACE (desc->albedo / normal / roughness /
  * metspec are written) instead of storing the gradients: per texel the 32 B of gradients are neither written nor
@@ -276,10 +297,11 @@ int pbr_normal_ingest(const PbrNormalDesc* desc, pbr_stream_t stream);
 int pbr_ingest_image(const PbrIngestDesc* desc, pbr_stream_t stream);
 int pbr_index_transform(const PbrIndexDesc* desc, pbr_stream_t stream);
 int pbr_adam_step(const PbrAdamDesc* desc, pbr_stream_t stream);
+int pbr_normal_op(const PbrNormalOpDesc* desc, pbr_stream_t stream);
 
 /* sizeof() of the descriptor structs as THIS library was compiled (binding self-check):
    which = 0 PbrPlane, 1 PbrCtDesc, 2 PbrCtGrads, 3 PbrCtLoss, 4 PbrConvDesc, 5 PbrBlendMap, 6 PbrBlendDesc,
-   7 PbrColorDesc, 8 PbrNormalDesc, 9 PbrIngestDesc, 10 PbrIndexMap, 11 PbrIndexDesc, 12 PbrAdamMap, 13 PbrAdamDesc, 14 PbrCtAdam;
+   7 PbrColorDesc, 8 PbrNormalDesc, 9 PbrIngestDesc, 10 PbrIndexMap, 11 PbrIndexDesc, 12 PbrAdamMap, 13 PbrAdamDesc, 14 PbrCtAdam, 15 PbrNormalOpDesc;
    anything else returns 0. */
 uint64_t pbr_sizeof(int which);
 

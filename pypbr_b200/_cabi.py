@@ -141,9 +141,19 @@ class PbrCtAdam(Structure):
     ]
 
 
+class PbrNormalOpDesc(Structure):
+    _fields_ = [
+        ("B", c_int32), ("H", c_int32), ("W", c_int32), ("op", c_int32),
+        ("cos_a", c_float), ("sin_a", c_float), ("scale", c_float), ("flip_y", c_int32),
+        ("in_", PbrPlane), ("out", PbrPlane),
+    ]
+
+
+NORMAL_OP_ROTATE, NORMAL_OP_FROM_HEIGHT = 0, 1
+
 # order = the `which` argument of pbr_sizeof()
 STRUCTS = (PbrPlane, PbrCtDesc, PbrCtGrads, PbrCtLoss, PbrConvDesc, PbrBlendMap, PbrBlendDesc, PbrColorDesc, PbrNormalDesc,
-           PbrIngestDesc, PbrIndexMap, PbrIndexDesc, PbrAdamMap, PbrAdamDesc, PbrCtAdam)
+           PbrIngestDesc, PbrIndexMap, PbrIndexDesc, PbrAdamMap, PbrAdamDesc, PbrCtAdam, PbrNormalOpDesc)
 
 _lib = None
 
@@ -151,7 +161,7 @@ _lib = None
 EXPORTS = (
     "pbr_abi_version", "pbr_strerror", "pbr_ct_forward", "pbr_ct_backward", "pbr_ct_loss_fwd_bwd", "pbr_ct_fit_step",
     "pbr_convert_m2s", "pbr_convert_s2m", "pbr_blend", "pbr_color_convert", "pbr_normal_min",
-    "pbr_normal_ingest", "pbr_ingest_image", "pbr_index_transform", "pbr_adam_step", "pbr_launch_count", "pbr_sizeof",
+    "pbr_normal_ingest", "pbr_ingest_image", "pbr_index_transform", "pbr_adam_step", "pbr_normal_op", "pbr_launch_count", "pbr_sizeof",
 )
 
 
@@ -190,6 +200,7 @@ def load():
     lib.pbr_ingest_image.argtypes = [POINTER(PbrIngestDesc), c_void_p]
     lib.pbr_index_transform.argtypes = [POINTER(PbrIndexDesc), c_void_p]
     lib.pbr_adam_step.argtypes = [POINTER(PbrAdamDesc), c_void_p]
+    lib.pbr_normal_op.argtypes = [POINTER(PbrNormalOpDesc), c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("pbr_strerror", "pbr_launch_count", "pbr_sizeof"):

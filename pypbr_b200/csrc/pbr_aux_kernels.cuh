@@ -202,4 +202,63 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// per-texel normal utilities of an augmentation pipeline
+//   ROTATE     : utils/functions.py:69-108 rotate_normals - (x, y) @ R(angle)^T, then F.normalize over the channels
+//   FROM_HEIGHT: utils/functions.py:123-177 compute_normal_from_height - one-sided differences of the zero-padded
+//                height map, (-gx*scale, -+gy*scale, 1), F.normalize
+// ------------------------------------------------------------------------------------------------
+struct NormalOpKParams {
+  PbrNormalOpDesc d;
+  int vec_ok;
+};
+
+__global__ void __launch_bounds__(kThreads) normal_op_kernel(const __grid_constant__ NormalOpKParams p) {
+  const PbrNormalOpDesc& d = p.d;
+  const Where w = locate(d.H, d.W, p.vec_ok != 0);
+  if (!w.active) return;
+  float o[3][kTexels];
+  if (d.op == PBR_NORMAL_OP_ROTATE) {
+    float v[3][kTexels];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) load_seg<kTexels>(d.in.ptr + plane_off(d.in, w.b, c, w.row, w.col0), w.vec, w.valid, v[c]);
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i) {
+      // row-vector times R^T with K = 2: a multiply and one fused multiply-add per output, as the GEMM computes it
+      const float rx = xfma(v[1][i], -d.sin_a, xmul(v[0][i], d.cos_a));
+      const float ry = xfma(v[1][i], d.cos_a, xmul(v[0][i], d.sin_a));
+      float o3[3];
+      normalize3(rx, ry, v[2][i], o3);
+      o[0][i] = o3[0]; o[1][i] = o3[1]; o[2][i] = o3[2];
+    }
+  } else {
+    // grad_x[x] = h[x-1] - h[x+1], grad_y[y] = h[y-1] - h[y+1], zero outside the image (F.pad)
+    const float* base = d.in.ptr + plane_off(d.in, w.b, 0, 0, 0);
+    const float* row = base + (int64_t)w.row * d.in.sh;
+    float c[kTexels + 2], up[kTexels], dn[kTexels];
+#pragma unroll
+    for (int i = 0; i < kTexels + 2; ++i) {
+      const int x = w.col0 + i - 1;
+      c[i] = (x >= 0 && x < d.W) ? __ldg(row + x) : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i) {
+      const int x = w.col0 + i;
+      const bool in = x < d.W;
+      up[i] = (in && w.row > 0) ? __ldg(row - d.in.sh + x) : 0.0f;
+      dn[i] = (in && w.row + 1 < d.H) ? __ldg(row + d.in.sh + x) : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i) {
+      const float gx = xmul(xsub(c[i], c[i + 2]), d.scale);
+      const float gy = xmul(xsub(up[i], dn[i]), d.scale);
+      float o3[3];
+      normalize3(-gx, d.flip_y ? gy : -gy, 1.0f, o3);
+      o[0][i] = o3[0]; o[1][i] = o3[1]; o[2][i] = o3[2];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) store_seg<kTexels>(d.out.ptr + plane_off(d.out, w.b, c, w.row, w.col0), w.vec, w.valid, o[c]);
+}
+
 }  // namespace pbr

@@ -200,6 +200,15 @@ __device__ __forceinline__ void stage_params(const CtKParams& p, CtStage& S) {
   __syncthreads();
 }
 
+// Generic Cook-Torrance kernels: the vector path is taken by the whole grid or not at all (W a multiple of the
+// texels per thread => no thread has a ragged segment), so the choice depends on kernel parameters only and compiles
+// to a uniform branch instead of predicated copies of both paths inside the light loop.
+__device__ __forceinline__ Where locate_ct(const CtKParams& p) {
+  Where w = locate_n<kCtTexels>(p.H, p.W, p.vec_ok != 0);
+  w.vec = p.vec_ok != 0 && (p.W % kCtTexels) == 0;
+  return w;
+}
+
 template <int WF>
 __device__ __forceinline__ void load_material(const CtKParams& p, const Where& w, int b, float (&araw)[3][kCtTexels],
                                               float (&nraw)[3][kCtTexels], float (&rough)[kCtTexels],
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kerne
   constexpr int G = PBR_FWD_GROUP;
   __shared__ CtStage S;
   stage_params(p, S);
-  const Where w = locate_n<kCtTexels>(p.H, p.W, p.vec_ok != 0);
+  const Where w = locate_ct(p);
   if (!w.active) return;
 
   V x[kSlots];
@@ -405,7 +414,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
     for (int i = tid; i < (p.flags.L + 1) * 3; i += kCtThreads) s_geo[i] = 0.0f;
   }
   stage_params(p, S);  // ends with __syncthreads()
-  const Where w = locate_n<kCtTexels>(p.H, p.W, p.vec_ok != 0);
+  const Where w = locate_ct(p);
   const float live = w.active ? 1.0f : 0.0f;
   if (!w.active && !int_grad && !is_loss && !kGeom) return;  // nothing to reduce: edge threads may leave
 
@@ -475,11 +484,13 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       constexpr int NT = kLanes * G;
       float* ring = s_ring + tid * NT;   // [slot][channel][thread][NT]
       const int nl_src = p.flags.per_light ? p.flags.L : 1;
+      const float* const gbase = p.gsrc.ptr + plane_off(p.gsrc, b, 0, w.row, w.col0 + kLanes * s);   // once per material
       auto issue = [&](int l) {
         if (l < nl_src) {
+          const float* const gl = gbase + (int64_t)l * p.gsrc_sl;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float* src = p.gsrc.ptr + plane_off(p.gsrc, b, c, w.row, w.col0 + kLanes * s) + (int64_t)l * p.gsrc_sl;
+            const float* src = gl + (int64_t)c * p.gsrc.sc;
             float* dst = ring + ((l % kRing) * 3 + c) * (kCtThreads * NT);
             if (NT == 2 && w.vec) {
               cp_async8(dst, src);
@@ -1189,6 +1200,7 @@ uint64_t pbr_sizeof(int which) {
     case 12: return sizeof(PbrAdamMap);
     case 13: return sizeof(PbrAdamDesc);
     case 14: return sizeof(PbrCtAdam);
+    case 15: return sizeof(PbrNormalOpDesc);
     default: return 0;
   }
 }
@@ -1418,6 +1430,21 @@ int pbr_adam_step(const PbrAdamDesc* d, pbr_stream_t stream) {
   dim3 grid, block;
   launch_shape(d->B, d->H, d->W, grid, block);
   adam_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);
+  return launch_result();
+}
+
+int pbr_normal_op(const PbrNormalOpDesc* d, pbr_stream_t stream) {
+  if (!d) return PBR_E_NULL;
+  if (int rc = check_dims(d->B, d->H, d->W)) return rc;
+  if (d->op != PBR_NORMAL_OP_ROTATE && d->op != PBR_NORMAL_OP_FROM_HEIGHT) return PBR_E_ENUM;
+  if (!d->in.ptr || !d->out.ptr) return PBR_E_NULL;
+  if (d->op == PBR_NORMAL_OP_FROM_HEIGHT && d->in.ptr == d->out.ptr) return PBR_E_NULL;   // a stencil cannot run in place
+  NormalOpKParams k{};
+  k.d = *d;
+  k.vec_ok = plane_vec_ok(d->out) && (d->op == PBR_NORMAL_OP_FROM_HEIGHT || plane_vec_ok(d->in));
+  dim3 grid, block;
+  launch_shape(d->B, d->H, d->W, grid, block);
+  normal_op_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);
   return launch_result();
 }
 

@@ -6,6 +6,16 @@
 
 #include "pbr_math.cuh"
 
+// light-loop unrolling of the forward evaluation (independent chains for the scheduler), tuned on the GPU
+#ifndef PBR_FWD_UNROLL
+#define PBR_FWD_UNROLL 1
+#endif
+#ifndef PBR_P1_UNROLL
+#define PBR_P1_UNROLL 2
+#endif
+namespace pbr {
+constexpr int kFwdUnroll = PBR_FWD_UNROLL, kP1Unroll = PBR_P1_UNROLL;
+}
 #ifndef PBR_MAX_LIGHTS
 #define PBR_MAX_LIGHTS 64
 #endif
@@ -176,6 +186,7 @@ PBR_HD void ct_forward_group(const CtStage& S, const CtFlags& F, const V (&araw)
     for (int i = 0; i < N; ++i) acc[c][i] = splat<V>(0.0f);
 
   const int L = (kLight == kLightPointHoisted) ? 1 : F.L;
+#pragma unroll kFwdUnroll
   for (int l = 0; l < L; ++l) {
     V outv[3][N];
 #pragma unroll
@@ -263,6 +274,7 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int i = 0; i < N; ++i) acc[c][i] = splat<V>(0.0f);
+#pragma unroll kP1Unroll
     for (int l = 0; l < L; ++l) {
 #pragma unroll
       for (int i = 0; i < N; ++i) {

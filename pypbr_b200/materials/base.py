@@ -19,6 +19,7 @@ material is being assembled on the host, with the same torch ops as the referenc
 from __future__ import annotations
 
 import copy
+import math
 from typing import Dict, List, Optional, Tuple, Union
 
 import numpy as np
@@ -26,7 +27,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import _cabi
-from ..utils import NormalConvention, linear_to_srgb, srgb_to_linear
+from ..utils import NormalConvention, compute_normal_from_height, linear_to_srgb, rotate_normals, srgb_to_linear
 
 try:  # PIL / torchvision are only needed for image ingestion and resize/crop
     from PIL import Image
@@ -389,9 +390,31 @@ class MaterialBase:
         return self._each(lambda _n, t: transform(t))
 
     def rotate(self, angle: float, expand: bool = False, padding_mode: str = "constant"):
-        raise NotImplementedError(
-            "pypbr_b200: rotate() is outside the shading hot path (SURVEY.md §8f rank 4); not built in this round."
-        )
+        """
+        Rotate all maps by `angle` degrees (pypbr/materials/base.py:539-603).  The resampling (pad, TF.rotate with
+        nearest-neighbour lookup, centre crop) is the reference's own sequence of library calls on the maps' device,
+        hence identical texel for texel; the normal VECTORS are then rotated by pbr_normal_op (rotate_normals,
+        utils/functions.py:69-108).
+        """
+        from torchvision.transforms import functional as TF
+
+        assert padding_mode in ["constant", "circular"], "Invalid padding mode. Must be 'constant' or 'circular'."
+        angle_rad = math.radians(angle)
+        for name, t in self._maps.items():
+            if t is None:
+                continue
+            height, width = t.shape[-2:]
+            if expand:
+                new_width = math.ceil(abs(width * math.cos(angle_rad)) + abs(height * math.sin(angle_rad)))
+                new_height = math.ceil(abs(width * math.sin(angle_rad)) + abs(height * math.cos(angle_rad)))
+                height, width = new_height, new_width
+            pad = math.ceil(math.sqrt(height**2 + width**2)) - height
+            padded = F.pad(t, (pad, pad, pad, pad), padding_mode)
+            rotated = TF.center_crop(TF.rotate(padded, angle, expand=True), (height, width)).contiguous()
+            if name == "normal":
+                rotated = rotate_normals(rotated, angle) if rotated.is_cuda else _rotate_normals_host(rotated, angle)
+            self._maps[name] = rotated
+        return self
 
     # ------------------------------------------------------------------ normal helpers
     def invert_normal(self):
@@ -415,7 +438,9 @@ class MaterialBase:
         return self
 
     def compute_normal_from_height(self, scale: float = 1.0):
-        raise NotImplementedError("pypbr_b200: compute_normal_from_height is outside the shading hot path (SURVEY.md §2 #8).")
+        """pypbr/materials/base.py:708-729: normal map from the height map (pbr_normal_op), in this material's convention."""
+        self._maps["normal"] = compute_normal_from_height(self._maps.get("height", None), scale, convention=self.normal_convention)
+        return self
 
     def compute_height_from_normal(self, scale: float = 1.0):
         raise NotImplementedError("pypbr_b200: compute_height_from_normal is outside the shading hot path (SURVEY.md §2 #8).")
@@ -484,6 +509,15 @@ class MaterialBase:
 
 
 # ---------------------------------------------------------------------- CUDA normal ingestion
+def _rotate_normals_host(normal: torch.Tensor, angle: float) -> torch.Tensor:
+    """rotate_normals (utils/functions.py:69-108) for a material still being assembled on the host (CPU tensors)."""
+    theta = math.radians(angle)
+    cd = _channel_dim(normal)
+    x, y, z = normal.unbind(cd)
+    rot = torch.stack([x * math.cos(theta) - y * math.sin(theta), x * math.sin(theta) + y * math.cos(theta), z], dim=cd)
+    return F.normalize(rot, dim=cd)
+
+
 def _normal_desc(t: torch.Tensor, out: Optional[torch.Tensor], channels: int) -> "_cabi.PbrNormalDesc":
     src = _cabi.rowmajor(t)
     B = src.shape[0] if src.dim() == 4 else 1

@@ -1,15 +1,20 @@
 """
-pypbr_b200.utils.functions — colour-space conversion behind the reference's names.
+pypbr_b200.utils.functions — colour-space conversion and the per-texel normal utilities behind the reference's names.
 
 `srgb_to_linear` / `linear_to_srgb` replace pypbr/utils/functions.py:31-66 with one streaming kernel
-(pbr_color_convert).  CUDA float32 tensors only: there is no CPU implementation in this package.
+(pbr_color_convert); `rotate_normals`, `compute_normal_from_height` replace pypbr/utils/functions.py:69-108 and
+:123-177 with pbr_normal_op; `invert_normal` is :111-120.  CUDA float32 tensors only: there is no CPU
+implementation in this package.
 """
 
 from __future__ import annotations
 
+import math
+
 import torch
 
 from .. import _cabi
+from .enums import NormalConvention
 
 
 class _ColorFn(torch.autograd.Function):
@@ -64,3 +69,60 @@ def linear_to_srgb(texture: torch.Tensor) -> torch.Tensor:
     if texture.requires_grad:
         return _ColorFn.apply(texture, False)
     return _color_convert(texture, False)
+
+
+def _normal_op(src: torch.Tensor, out: torch.Tensor, op: int, cos_a=0.0, sin_a=0.0, scale=0.0, flip_y=0) -> torch.Tensor:
+    lib = _cabi.load()
+    B = src.shape[0] if src.dim() == 4 else 1
+    d = _cabi.PbrNormalOpDesc(B, src.shape[-2], src.shape[-1], op, cos_a, sin_a, scale, flip_y, _cabi.plane(src), _cabi.plane(out))
+    with torch.cuda.device(src.device):
+        _cabi.check(lib.pbr_normal_op(_cabi.byref(d), _cabi.stream_ptr(src.device)), "pbr_normal_op")
+    return out
+
+
+def rotate_normals(normal_map: torch.Tensor, angle: float) -> torch.Tensor:
+    """
+    Rotate the (x, y) part of every normal by `angle` degrees and renormalise (pypbr/utils/functions.py:69-108).
+    Like the reference, the map is modified IN PLACE and returned.  (3,H,W) or (B,3,H,W).
+    """
+    _cabi.require_cuda(normal_map, "normal_map")
+    if normal_map.dim() not in (3, 4) or normal_map.shape[-3] != 3:
+        raise ValueError(f"normal_map must have shape (3, H, W) or (B, 3, H, W), got {tuple(normal_map.shape)}")
+    theta = math.radians(angle)
+    target = normal_map.detach()
+    work = _cabi.rowmajor(target)
+    _normal_op(work, work, _cabi.NORMAL_OP_ROTATE, cos_a=math.cos(theta), sin_a=math.sin(theta))
+    if work.data_ptr() != target.data_ptr():   # W-strided view: the kernel worked on a packed copy
+        target.copy_(work)
+    return normal_map
+
+
+def invert_normal(normals: torch.Tensor) -> torch.Tensor:
+    """Flip the Y component in place (pypbr/utils/functions.py:111-120)."""
+    if normals is not None:
+        normals.select(-3, 1).neg_()
+    return normals
+
+
+def compute_normal_from_height(height_map: torch.Tensor, scale: float = 1.0,
+                               convention: NormalConvention = NormalConvention.OPENGL) -> torch.Tensor:
+    """
+    Normal map from a height map (pypbr/utils/functions.py:123-177): one-sided differences of the zero-padded
+    height, (-gx*scale, -gy*scale, 1) for OpenGL, (-gx*scale, +gy*scale, 1) for DirectX, normalised.
+    (H,W) or (1,H,W) -> (3,H,W); (B,1,H,W) -> (B,3,H,W).
+    """
+    if height_map is None:
+        raise ValueError("Height map is required to compute normals.")
+    if convention not in (NormalConvention.OPENGL, NormalConvention.DIRECTX):
+        raise ValueError("Unsupported normal convention.")
+    _cabi.require_cuda(height_map, "height_map")
+    if height_map.dim() == 2:
+        height_map = height_map.unsqueeze(0)
+    if height_map.dim() not in (3, 4) or height_map.shape[-3] != 1:
+        raise ValueError(f"height_map must have shape (H, W), (1, H, W) or (B, 1, H, W), got {tuple(height_map.shape)}")
+    src = _cabi.rowmajor(height_map.detach())
+    shape = list(src.shape)
+    shape[-3] = 3
+    out = torch.empty(shape, dtype=torch.float32, device=src.device)
+    return _normal_op(src, out, _cabi.NORMAL_OP_FROM_HEIGHT, scale=float(scale),
+                      flip_y=1 if convention == NormalConvention.DIRECTX else 0)

@@ -757,3 +757,64 @@ def test_fused_loss_step_delivers_shared_parameter_gradients():
                            (buf[1 + 6 * L:], v64.grad, "view")):
         want = want.numpy().reshape(-1)
         assert np.all(np.abs(got - want) <= _shared_tol(want)), (key, got, want)
+
+
+def test_normal_from_height_and_rotate_match_reference_ops():
+    """compute_normal_from_height (utils/functions.py:123-177) and rotate / rotate_normals
+    (base.py:539-603, utils/functions.py:69-108) against the reference's sequence of torch ops, restated here."""
+    import math
+    import torch.nn.functional as F
+    from torchvision.transforms import functional as TF
+
+    from pypbr_b200.materials import BasecolorMetallicMaterial
+    from pypbr_b200.utils import NormalConvention, compute_normal_from_height, rotate_normals
+
+    g = torch.Generator().manual_seed(8)
+    for shape in ((1, 37, 53), (1, 64, 64), (1, 1, 5), (1, 6, 1)):
+        h = torch.rand(shape, generator=g)
+        for conv in (NormalConvention.OPENGL, NormalConvention.DIRECTX):
+            for scale in (1.0, 7.5):
+                gx = (F.pad(h, (1, 0, 0, 0))[:, :, :-1] - F.pad(h, (0, 1, 0, 0))[:, :, 1:]) * scale
+                gy = (F.pad(h, (0, 0, 1, 0))[:, :-1, :] - F.pad(h, (0, 0, 0, 1))[:, 1:, :]) * scale
+                want = F.normalize(torch.cat([-gx, -gy if conv == NormalConvention.OPENGL else gy, torch.ones_like(h)], dim=0), dim=0)
+                got = compute_normal_from_height(h.to(DEV), scale, conv).cpu()
+                assert got.shape == want.shape
+                assert bool(((got - want).abs() <= 1.2e-7 * want.abs() + 1e-9).all()), (shape, float((got - want).abs().max()))
+    hb = torch.rand(3, 1, 20, 28, generator=g)   # batched = per-material calls
+    nb = compute_normal_from_height(hb.to(DEV), 2.0)
+    for b in range(3):
+        assert torch.equal(nb[b], compute_normal_from_height(hb[b].to(DEV), 2.0))
+    assert torch.equal(compute_normal_from_height(hb[0, 0].to(DEV)), compute_normal_from_height(hb[0].to(DEV)))
+    with pytest.raises(ValueError):
+        compute_normal_from_height(None)
+
+    n = F.normalize(torch.randn(3, 33, 47, generator=g) * torch.tensor([0.4, 0.4, 0.1]).view(3, 1, 1) + torch.tensor([0.0, 0.0, 1.0]).view(3, 1, 1), dim=0)
+    for angle in (30.0, -75.0, 180.0):
+        th = math.radians(angle)
+        R = torch.tensor([[math.cos(th), -math.sin(th)], [math.sin(th), math.cos(th)]])
+        xy = torch.stack([n[0].reshape(-1), n[1].reshape(-1)], dim=1) @ R.T
+        want = F.normalize(torch.stack([xy[:, 0], xy[:, 1], n[2].reshape(-1)], dim=1), dim=1).T.reshape(3, 33, 47)
+        t = n.clone().to(DEV)
+        got = rotate_normals(t, angle)
+        assert got.data_ptr() == t.data_ptr()   # in place, like the reference
+        assert bool(((got.cpu() - want).abs() <= 1e-6 * want.abs() + 2e-7).all()), float((got.cpu() - want).abs().max())
+
+    # material.rotate: resampling through the same library calls as the reference + the vector rotation
+    maps, _, _, _ = _random_case(12, None, 40, 56, 1)
+    mat, _ = _material(maps, dict(light_type="point"))
+    mat.rotate(33.0, expand=False, padding_mode="circular")
+    ref = {}
+    for k, v in maps.items():
+        pad = math.ceil(math.sqrt(40**2 + 56**2)) - 40
+        r = TF.center_crop(TF.rotate(F.pad(v.to(DEV), (pad, pad, pad, pad), "circular"), 33.0, expand=True), (40, 56)).contiguous()
+        ref[k] = r
+    for k in ("albedo", "roughness", "metallic"):
+        assert torch.equal(mat._maps[k], ref[k]), k
+    th = math.radians(33.0)
+    rn = ref["normal"].cpu()
+    want = F.normalize(torch.stack([rn[0] * math.cos(th) - rn[1] * math.sin(th), rn[0] * math.sin(th) + rn[1] * math.cos(th), rn[2]]), dim=0)
+    assert bool(((mat._maps["normal"].cpu() - want).abs() <= 1e-6 * want.abs() + 2e-7).all())
+    m2 = BasecolorMetallicMaterial(albedo_is_srgb=True, device=DEV)
+    m2._maps["height"] = torch.rand(1, 16, 16, generator=g).to(DEV)
+    m2.compute_normal_from_height(3.0)
+    assert m2._maps["normal"].shape == (3, 16, 16)

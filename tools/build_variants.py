@@ -25,14 +25,14 @@ VARIANTS = {
     "g_t256x2_f3b1": v(ct_threads=256, fwd_min_ctas=3, bwd_min_ctas=1),
     "g_t64x2_f8b6": v(ct_threads=64, fwd_min_ctas=8, bwd_min_ctas=6),
     "g_t64x2_f10b5": v(ct_threads=64, fwd_min_ctas=10, bwd_min_ctas=5),
-    # geometry cache of the multi-light kernels (point lights, L > 1): fields cached / off / CTAs per SM
+    # geometry cache of the multi-light kernels (point lights, L > 1): off / backward register budget / light-loop unrolling
     "gc_off": ["-DPBR_GC_MAX_BYTES=0"],
-    "gc7": ["-DPBR_GC_FIELDS=7"],
-    "gc8": ["-DPBR_GC_FIELDS=8"],
-    "gc6_f3b2": v(fwd_min_ctas=3, bwd_min_ctas=2),
-    "gc8_f3b2": ["-DPBR_GC_FIELDS=8"] + v(fwd_min_ctas=3, bwd_min_ctas=2),
-    "gc6_t64": v(ct_threads=64, fwd_min_ctas=8, bwd_min_ctas=6),
-    "gc6_m32": v(hoist_mats=32),
+    "gc_b3": v(bwd_cached_min_ctas=3),
+    "u_f2": v(fwd_unroll=2),
+    "u_p2": v(p1_unroll=2),
+    "u_f2p2": v(fwd_unroll=2, p1_unroll=2),
+    "u_f2_f3": v(fwd_unroll=2, fwd_min_ctas=3),
+    "u_f4_f2": v(fwd_unroll=4, fwd_min_ctas=2),
     # memory pipeline only (no shading math): the floor of the TMA-in / STG-out design
     "nomath": ["-DPBR_DBG_NOMATH"],
 }
