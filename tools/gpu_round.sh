@@ -11,6 +11,8 @@ SMI=$!
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_c2.log 2>gpurun_out/bench_c2.err; echo "bench c2 rc=$?"; cat gpurun_out/bench_c2.log
 kill $SMI
 for c in c3 c5; do timeout 600 python bench.py --config $c --steps 5 --warmup 3 --no-e2e > gpurun_out/bench_$c.log 2>gpurun_out/bench_$c.err; echo "bench $c rc=$?"; cat gpurun_out/bench_$c.log; done
+timeout 600 python bench.py --config c5 --fit two-kernel --steps 5 --warmup 3 --no-e2e > gpurun_out/bench_c5_two_kernel.log 2>gpurun_out/bench_c5_two_kernel.err; echo "bench c5 two-kernel rc=$?"; cat gpurun_out/bench_c5_two_kernel.log
+timeout 600 python bench.py --config aux > gpurun_out/bench_aux.log 2>gpurun_out/bench_aux.err; echo "bench aux rc=$?"; cat gpurun_out/bench_aux.log
 timeout 600 python bench.py --config c4 --steps 10 --warmup 3 > gpurun_out/bench_c4.log 2>gpurun_out/bench_c4.err; echo "bench c4 rc=$?"; cat gpurun_out/bench_c4.log
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.log 2>gpurun_out/bench_ref.err; echo "bench ref rc=$?"; cat gpurun_out/bench_ref.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/${R}_launches_c2.csv python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
