@@ -248,15 +248,19 @@ typedef struct PbrAdamDesc {
  *                grad_y = h[y-1] - h[y+1] with zeros outside the image, normal = normalize(-gx*scale, -gy*scale, 1)
  *                (flip_y = 0, OpenGL convention) or (-gx*scale, +gy*scale, 1) (flip_y = 1, DirectX).  `in` has 1 channel;
  *                in and out must not overlap.
+ *   DIVERGENCE : the per-texel half of compute_height_from_normal, pypbr/utils/functions.py:211-283: the gradient field
+ *                g = (-Nx, -Ny | +Ny) / (Nz + 1e-8) * scale (flip_y as above) and its forward-difference divergence with
+ *                replicate padding.  `in` has 3 channels, `out` ONE channel; in and out must not overlap.  The Poisson
+ *                solve that follows (utils/functions.py:286-323) is two FFT library calls and stays with the caller.
  */
-enum { PBR_NORMAL_OP_ROTATE = 0, PBR_NORMAL_OP_FROM_HEIGHT = 1 };
+enum { PBR_NORMAL_OP_ROTATE = 0, PBR_NORMAL_OP_FROM_HEIGHT = 1, PBR_NORMAL_OP_DIVERGENCE = 2 };
 typedef struct PbrNormalOpDesc {
   int32_t B, H, W;
   int32_t op;               /* PBR_NORMAL_OP_* */
   float cos_a, sin_a;       /* ROTATE */
-  float scale;              /* FROM_HEIGHT */
-  int32_t flip_y;           /* FROM_HEIGHT: 1 = NormalConvention.DIRECTX */
-  PbrPlane in, out;         /* out: 3 ch */
+  float scale;              /* FROM_HEIGHT, DIVERGENCE */
+  int32_t flip_y;           /* FROM_HEIGHT, DIVERGENCE: 1 = NormalConvention.DIRECTX */
+  PbrPlane in, out;         /* out: 3 ch (DIVERGENCE: 1 ch) */
 } PbrNormalOpDesc;
 
 /*

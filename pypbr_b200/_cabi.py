@@ -149,7 +149,7 @@ class PbrNormalOpDesc(Structure):
     ]
 
 
-NORMAL_OP_ROTATE, NORMAL_OP_FROM_HEIGHT = 0, 1
+NORMAL_OP_ROTATE, NORMAL_OP_FROM_HEIGHT, NORMAL_OP_DIVERGENCE = 0, 1, 2
 
 # order = the `which` argument of pbr_sizeof()
 STRUCTS = (PbrPlane, PbrCtDesc, PbrCtGrads, PbrCtLoss, PbrConvDesc, PbrBlendMap, PbrBlendDesc, PbrColorDesc, PbrNormalDesc,

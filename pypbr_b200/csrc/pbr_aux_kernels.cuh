@@ -207,6 +207,9 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ 
 //   ROTATE     : utils/functions.py:69-108 rotate_normals - (x, y) @ R(angle)^T, then F.normalize over the channels
 //   FROM_HEIGHT: utils/functions.py:123-177 compute_normal_from_height - one-sided differences of the zero-padded
 //                height map, (-gx*scale, -+gy*scale, 1), F.normalize
+//   DIVERGENCE : utils/functions.py:211-283, the per-texel half of compute_height_from_normal - the gradient field
+//                g = (-Nx, -+Ny) / (Nz + 1e-8) * scale and its forward-difference divergence with replicate padding
+//                (the Poisson solve that follows is two cuFFT calls on the host side)
 // ------------------------------------------------------------------------------------------------
 struct NormalOpKParams {
   PbrNormalOpDesc d;
@@ -218,6 +221,29 @@ __global__ void __launch_bounds__(kThreads) normal_op_kernel(const __grid_consta
   const Where w = locate(d.H, d.W, p.vec_ok != 0);
   if (!w.active) return;
   float o[3][kTexels];
+  if (d.op == PBR_NORMAL_OP_DIVERGENCE) {
+    // div[y][x] = (gx[y][x+1] - gx[y][x]) + (gy[y+1][x] - gy[y][x]); the replicated last column / row differences are 0
+    const float* nx = d.in.ptr + plane_off(d.in, w.b, 0, w.row, 0);
+    const float* ny = d.in.ptr + plane_off(d.in, w.b, 1, w.row, 0);
+    const float* nz = d.in.ptr + plane_off(d.in, w.b, 2, w.row, 0);
+    const bool has_dn = w.row + 1 < d.H;
+    float gx[kTexels + 1], div[kTexels];
+#pragma unroll
+    for (int i = 0; i < kTexels + 1; ++i) {
+      const int x = min(w.col0 + i, d.W - 1);
+      gx[i] = xmul(xdiv(-__ldg(nx + x), xadd(__ldg(nz + x), 1e-8f)), d.scale);
+    }
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i) {
+      const int x = min(w.col0 + i, d.W - 1);
+      const float y0 = __ldg(ny + x), z0 = xadd(__ldg(nz + x), 1e-8f);
+      const float y1 = has_dn ? __ldg(ny + d.in.sh + x) : y0, z1 = has_dn ? xadd(__ldg(nz + d.in.sh + x), 1e-8f) : z0;
+      const float gy0 = xmul(xdiv(d.flip_y ? y0 : -y0, z0), d.scale), gy1 = xmul(xdiv(d.flip_y ? y1 : -y1, z1), d.scale);
+      div[i] = xadd(xsub(gx[i + 1], gx[i]), xsub(gy1, gy0));
+    }
+    store_seg<kTexels>(d.out.ptr + plane_off(d.out, w.b, 0, w.row, w.col0), w.vec, w.valid, div);
+    return;
+  }
   if (d.op == PBR_NORMAL_OP_ROTATE) {
     float v[3][kTexels];
 #pragma unroll

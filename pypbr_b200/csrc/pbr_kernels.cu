@@ -1436,12 +1436,12 @@ int pbr_adam_step(const PbrAdamDesc* d, pbr_stream_t stream) {
 int pbr_normal_op(const PbrNormalOpDesc* d, pbr_stream_t stream) {
   if (!d) return PBR_E_NULL;
   if (int rc = check_dims(d->B, d->H, d->W)) return rc;
-  if (d->op != PBR_NORMAL_OP_ROTATE && d->op != PBR_NORMAL_OP_FROM_HEIGHT) return PBR_E_ENUM;
+  if (d->op < PBR_NORMAL_OP_ROTATE || d->op > PBR_NORMAL_OP_DIVERGENCE) return PBR_E_ENUM;
   if (!d->in.ptr || !d->out.ptr) return PBR_E_NULL;
-  if (d->op == PBR_NORMAL_OP_FROM_HEIGHT && d->in.ptr == d->out.ptr) return PBR_E_NULL;   // a stencil cannot run in place
+  if (d->op != PBR_NORMAL_OP_ROTATE && d->in.ptr == d->out.ptr) return PBR_E_NULL;   // a stencil cannot run in place
   NormalOpKParams k{};
   k.d = *d;
-  k.vec_ok = plane_vec_ok(d->out) && (d->op == PBR_NORMAL_OP_FROM_HEIGHT || plane_vec_ok(d->in));
+  k.vec_ok = plane_vec_ok(d->out) && (d->op != PBR_NORMAL_OP_ROTATE || plane_vec_ok(d->in));
   dim3 grid, block;
   launch_shape(d->B, d->H, d->W, grid, block);
   normal_op_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);

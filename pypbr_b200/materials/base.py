@@ -27,7 +27,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import _cabi
-from ..utils import NormalConvention, compute_normal_from_height, linear_to_srgb, rotate_normals, srgb_to_linear
+from ..utils import NormalConvention, compute_height_from_normal, compute_normal_from_height, linear_to_srgb, rotate_normals, srgb_to_linear
 
 try:  # PIL / torchvision are only needed for image ingestion and resize/crop
     from PIL import Image
@@ -443,7 +443,9 @@ class MaterialBase:
         return self
 
     def compute_height_from_normal(self, scale: float = 1.0):
-        raise NotImplementedError("pypbr_b200: compute_height_from_normal is outside the shading hot path (SURVEY.md §2 #8).")
+        """pypbr/materials/base.py:731-751: height map from the normal map (pbr_normal_op DIVERGENCE + cuFFT Poisson solve)."""
+        self._maps["height"] = compute_height_from_normal(self._maps.get("normal", None), scale, convention=self.normal_convention)
+        return self
 
     # ------------------------------------------------------------------ colour space
     def to_linear(self):

@@ -3,7 +3,8 @@ pypbr_b200.utils.functions — colour-space conversion and the per-texel normal 
 
 `srgb_to_linear` / `linear_to_srgb` replace pypbr/utils/functions.py:31-66 with one streaming kernel
 (pbr_color_convert); `rotate_normals`, `compute_normal_from_height` replace pypbr/utils/functions.py:69-108 and
-:123-177 with pbr_normal_op; `invert_normal` is :111-120.  CUDA float32 tensors only: there is no CPU
+:123-177 with pbr_normal_op; `invert_normal` is :111-120; `compute_height_from_normal` (:180-323) runs its per-texel half (gradient field + divergence)
+in pbr_normal_op and the Poisson solve as two cuFFT calls.  CUDA float32 tensors only: there is no CPU
 implementation in this package.
 """
 
@@ -126,3 +127,35 @@ def compute_normal_from_height(height_map: torch.Tensor, scale: float = 1.0,
     out = torch.empty(shape, dtype=torch.float32, device=src.device)
     return _normal_op(src, out, _cabi.NORMAL_OP_FROM_HEIGHT, scale=float(scale),
                       flip_y=1 if convention == NormalConvention.DIRECTX else 0)
+
+
+def compute_height_from_normal(normal_map: torch.Tensor, scale: float = 1.0,
+                               convention: NormalConvention = NormalConvention.OPENGL) -> torch.Tensor:
+    """
+    Height map from a normal map by Poisson reconstruction (pypbr/utils/functions.py:180-323), (3,H,W) -> (1,H,W) in
+    [0,1].  The gradient field (-Nx, -+Ny)/(Nz + 1e-8)*scale and its forward-difference divergence are one kernel
+    (pbr_normal_op DIVERGENCE); the solve divides the 2-D FFT of the divergence by the eigenvalues of the periodic
+    5-point Laplacian, 2cos(2 pi x/W) + 2cos(2 pi y/H) - 4, with the zero frequency removed (cuFFT through torch.fft);
+    the result is shifted and scaled to [0, 1] like the reference does.
+    """
+    if normal_map is None:
+        raise ValueError("Normal map is required to compute height.")
+    if normal_map.shape[0] != 3:
+        raise ValueError("Normal map must have three channels.")
+    if convention not in (NormalConvention.OPENGL, NormalConvention.DIRECTX):
+        raise ValueError("Unsupported normal convention.")
+    _cabi.require_cuda(normal_map, "normal_map")
+    src = _cabi.rowmajor(normal_map.detach())
+    H, W = src.shape[-2:]
+    div = torch.empty((1, H, W), dtype=torch.float32, device=src.device)
+    _normal_op(src, div, _cabi.NORMAL_OP_DIVERGENCE, scale=float(scale), flip_y=1 if convention == NormalConvention.DIRECTX else 0)
+    wy = 2 * math.pi * torch.arange(H, dtype=torch.float32, device=src.device).view(-1, 1) / H
+    wx = 2 * math.pi * torch.arange(W, dtype=torch.float32, device=src.device).view(1, -1) / W
+    eig = (2 * torch.cos(wx) - 2) + (2 * torch.cos(wy) - 2)
+    eig[0, 0] = 1.0
+    spec = torch.fft.fft2(div[0]) / eig
+    spec[0, 0] = 0
+    height = torch.fft.ifft2(spec).real
+    height = height - height.mean()
+    lo, hi = height.min(), height.max()
+    return ((height - lo) / (hi - lo + 1e-8)).unsqueeze(0)

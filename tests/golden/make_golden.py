@@ -369,8 +369,31 @@ def make_geomgrad_cases():
     np.savez_compressed(os.path.join(HERE, "geomgrad_shared_params.npz"), **arrs)
 
 
+def make_height_from_normal_fixture():
+    """compute_height_from_normal / compute_normal_from_height of the reference itself (utils/functions.py:123-323)."""
+    from pypbr.utils import NormalConvention as RefConv
+    from pypbr.utils import compute_height_from_normal as ref_h_from_n
+    from pypbr.utils import compute_normal_from_height as ref_n_from_h
+
+    gen = torch.Generator().manual_seed(606)
+    H, W = 48, 72
+    yy, xx = torch.meshgrid(torch.linspace(0, 3.0, H), torch.linspace(0, 5.0, W), indexing="ij")
+    height = 0.5 + 0.25 * torch.sin(2.1 * xx) * torch.cos(1.3 * yy) + 0.05 * torch.rand(H, W, generator=gen)
+    height = height.unsqueeze(0)
+    arrs = {"height": height.numpy()}
+    for conv, tag in ((RefConv.OPENGL, "gl"), (RefConv.DIRECTX, "dx")):
+        n = ref_n_from_h(height, 4.0, conv)
+        arrs[f"normal_{tag}"] = n.numpy()
+        arrs[f"height_back_{tag}"] = ref_h_from_n(n.clone(), 1.0, conv).numpy()
+    np.savez_compressed(os.path.join(HERE, "height_normal_48x72.npz"), **arrs)
+    print("height_normal_48x72: ok")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "height":
+        make_height_from_normal_fixture()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "geomgrad":   # only this fixture (the others are unchanged)
         make_geomgrad_cases()
         sys.exit(0)
@@ -380,3 +403,4 @@ if __name__ == "__main__":
     make_blend_cases()
     make_config1_fixture()
     make_geomgrad_cases()
+    make_height_from_normal_fixture()

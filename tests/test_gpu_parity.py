@@ -818,3 +818,49 @@ def test_normal_from_height_and_rotate_match_reference_ops():
     m2._maps["height"] = torch.rand(1, 16, 16, generator=g).to(DEV)
     m2.compute_normal_from_height(3.0)
     assert m2._maps["normal"].shape == (3, 16, 16)
+
+
+def test_height_normal_round_trip_matches_reference_fixture():
+    """tests/golden/height_normal_48x72.npz: compute_normal_from_height and compute_height_from_normal of the REFERENCE
+    (utils/functions.py:123-323), both conventions.  The divergence kernel is also checked bit for bit against the
+    reference's op sequence restated with torch (replicate-padded forward differences)."""
+    import os
+
+    import torch.nn.functional as F
+
+    from conftest import GOLDEN
+    from pypbr_b200 import _cabi
+    from pypbr_b200.materials import BasecolorMetallicMaterial
+    from pypbr_b200.utils import NormalConvention, compute_height_from_normal, compute_normal_from_height
+    from pypbr_b200.utils.functions import _normal_op
+
+    z = np.load(os.path.join(GOLDEN, "height_normal_48x72.npz"))
+    height = torch.from_numpy(z["height"]).to(DEV)
+    for conv, tag in ((NormalConvention.OPENGL, "gl"), (NormalConvention.DIRECTX, "dx")):
+        n = compute_normal_from_height(height, 4.0, conv)
+        want_n = torch.from_numpy(z[f"normal_{tag}"])
+        assert bool(((n.cpu() - want_n).abs() <= 1.2e-7 * want_n.abs() + 1e-9).all())
+        nref = want_n.to(DEV)
+        # divergence: bit-exact against the same chain of individually rounded ops
+        nz = want_n[2] + 1e-8
+        gx = (-want_n[0] / nz) * 1.0
+        gy = ((-want_n[1] if conv == NormalConvention.OPENGL else want_n[1]) / nz) * 1.0
+        gxp = F.pad(gx[None, None], (0, 1, 0, 0), mode="replicate")[0, 0]
+        gyp = F.pad(gy[None, None], (0, 0, 0, 1), mode="replicate")[0, 0]
+        want_div = (gxp[:, 1:] - gxp[:, :-1]) + (gyp[1:, :] - gyp[:-1, :])
+        div = torch.empty(1, *want_div.shape, device=DEV)
+        _normal_op(nref, div, _cabi.NORMAL_OP_DIVERGENCE, scale=1.0, flip_y=int(conv == NormalConvention.DIRECTX))
+        assert torch.equal(div[0].cpu(), want_div)
+        # the whole reconstruction (cuFFT vs the reference's CPU FFT): heights are normalised to [0, 1]
+        h = compute_height_from_normal(nref, 1.0, conv)
+        want_h = torch.from_numpy(z[f"height_back_{tag}"])
+        assert h.shape == want_h.shape == (1, 48, 72)
+        assert float((h.cpu() - want_h).abs().max()) <= 2e-5
+    m = BasecolorMetallicMaterial(albedo_is_srgb=True, device=DEV)
+    m._maps["normal"] = torch.from_numpy(z["normal_gl"]).to(DEV)
+    m.compute_height_from_normal()
+    assert float((m._maps["height"].cpu() - torch.from_numpy(z["height_back_gl"])).abs().max()) <= 2e-5
+    with pytest.raises(ValueError):
+        compute_height_from_normal(None)
+    with pytest.raises(ValueError):
+        compute_height_from_normal(torch.zeros(2, 4, 4, device=DEV))
