@@ -98,6 +98,10 @@ typedef struct PbrCtGrads {
      zero-fills), may be NULL.  Requesting either selects the generic kernels with per-texel light geometry. */
   float* d_lights;          /* L*3: w.r.t. PbrCtDesc.lights as passed (raw direction or position) */
   float* d_view;            /* 3:   w.r.t. PbrCtDesc.view as passed (not normalised) */
+  /* Optional (ptr may be NULL): the output pbr_ct_forward wrote for the same descriptor.  Used in accumulate mode with
+     L > 1 only: the gate of clamp(sum over lights) and the slope of the sRGB encode are derived from it, which saves the
+     backward a complete second forward evaluation of every light (otherwise it recomputes the sum first: two passes). */
+  PbrPlane fwd_out;
 } PbrCtGrads;
 
 /*

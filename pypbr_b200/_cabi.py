@@ -55,6 +55,7 @@ class PbrCtGrads(Structure):
         ("grad_out", PbrPlane), ("grad_out_sl", c_int64),
         ("d_albedo", PbrPlane), ("d_normal", PbrPlane), ("d_roughness", PbrPlane), ("d_metspec", PbrPlane),
         ("d_intensity", c_void_p), ("d_lights", c_void_p), ("d_view", c_void_p),
+        ("fwd_out", PbrPlane),
     ]
 
 

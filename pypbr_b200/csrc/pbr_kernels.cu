@@ -160,6 +160,7 @@ struct CtKParams {
   // backward: `gsrc` is grad_out, or the target image when is_loss
   PbrPlane gsrc;
   int64_t gsrc_sl;
+  PbrPlane fout;         // backward, accumulate mode, L > 1: the forward launch's output (optional: single-pass backward)
   PbrPlane d_albedo, d_normal, d_roughness, d_metspec;
   float* d_intensity;
   float* d_lights;       // L*3: d/d light position (point) or raw direction (directional); geometry-gradient kernels
@@ -377,6 +378,23 @@ __device__ __forceinline__ float warp_sum(float v) {
 #endif
 constexpr int bwd_min_ctas(int light_mode) { return light_mode == kLightPointCached ? PBR_BWD_CACHED_MIN_CTAS : PBR_BWD_MIN_CTAS; }
 
+// The saved forward output of the material / row segment being back-propagated (PbrCtGrads.fwd_out).
+struct CtaSavedOut {
+  const CtKParams& p;
+  const Where& w;
+  int b, s, vs;
+  __device__ __forceinline__ bool have() const { return p.fout.ptr != nullptr; }
+  template <int G>
+  __device__ __forceinline__ void operator()(V (&o)[3][G]) const {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float tv[kLanes * G];
+      load_seg<kLanes * G>(p.fout.ptr + plane_off(p.fout, b, c, w.row, w.col0 + kLanes * s), w.vec, vs, tv);
+      pairs_of<G>(tv, 0, o[c]);
+    }
+  }
+};
+
 // Sink of the geometry gradients (kGeom kernels): warp shuffle -> shared atomics, flushed once per CTA.
 struct CtaGeomSink {
   static constexpr bool kOn = true;
@@ -551,9 +569,10 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       gcs.base += s * gc.stride;
       if constexpr (kGeom) {
         ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs,
-                                            CtaGeomSink{s_geo, p.flags.L, tid, live});
+                                            CtaGeomSink{s_geo, p.flags.L, tid, live}, CtaSavedOut{p, w, b, s, vs});
       } else {
-        ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs);
+        ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs,
+                                            NoGeomSink(), CtaSavedOut{p, w, b, s, vs});
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) { unpair_to<G>(da[c], s, d_albedo[c]); unpair_to<G>(dn[c], s, d_normal[c]); unpair_to<G>(dm[c], s, d_met[c]); }
@@ -1223,6 +1242,10 @@ int pbr_ct_backward(const PbrCtDesc* desc, const PbrCtGrads* grads, pbr_stream_t
   k.gsrc = grads->grad_out; k.gsrc_sl = grads->grad_out_sl;
   k.is_loss = 0;
   k.vec_ok = k.vec_ok && plane_vec_ok(grads->grad_out) && (grads->grad_out_sl % kTexels == 0);
+  if (!desc->per_light && desc->L > 1) {   // only the accumulate-mode backward of several lights has a use for it
+    k.fout = grads->fwd_out;
+    k.vec_ok = k.vec_ok && plane_vec_ok(grads->fwd_out);
+  }
   return ct_dispatch(k, kernel_workflow(desc), true, (cudaStream_t)stream);
 }
 

@@ -237,13 +237,41 @@ struct NoGeomSink {
   PBR_HD void view(const float (&)[3]) const {}
 };
 
+//   saved_out                   : accumulate mode with L > 1 only.  saved_out.have() (uniform over the kernel): the
+//        encoded output of the FORWARD launch is at hand (what autograd keeps anyway) and saved_out(out[3][N]) loads it;
+//        the gate of clamp(sum) and the slope of the encode are then derived from it and pass 1 - a complete second
+//        forward evaluation of every light - is skipped.
+struct NoSavedOut {
+  PBR_HD bool have() const { return false; }
+  template <class V, int N>
+  PBR_HD void operator()(V (&)[3][N]) const {}
+};
+
+// d encode(clamp(acc)) / d acc from out = encode(clamp(acc)) (utils/functions.py:50-66 inverted on its upper branch:
+// t^(1/2.4 - 1) = u^-1.4 with u = (out + 0.055)/1.055).  out >= encode(1) - which is 0.99999994, not 1, in fp32:
+// 1.055 - 0.055 rounds down, in the reference too - is read as "the sum was clamped": the one or two fp32 values of the
+// sum just below 1 that encode to the same number lose their gradient (the tolerant-zone rounding of the sum already
+// moves that boundary by more than this).
+template <class V>
+PBR_HD V encode_slope_from_out(V out, bool return_srgb) {
+  V slope = splat<V>(1.0f);
+  float top = 1.0f;   // what the forward wrote wherever the sum reached 1
+  if (return_srgb) {
+    V u = out * kInv1_055 + (0.055f * kInv1_055);
+    slope = vsel(vle(out, 12.92f * kSrgbEncKnee), 12.92f, (1.055f * 0.416666657f) * pow_pos(u, -1.4f));
+    top = srgb_encode<false, float>(1.0f, nullptr);
+  }
+  return vsel(vge(out, top), 0.0f, slope);
+}
+
 template <int kWorkflow, int kLight, class V, int N, class Gout, class IntSink, class Fetch = NoFetch,
-          class GeomSink = NoGeomSink>
+          class GeomSink = NoGeomSink, class SavedOut = NoSavedOut>
 PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw)[3][N], const V (&nraw)[3][N],
                               const V (&rough)[N], const V (&mraw)[3][N], const V (&x)[N], float y,
                               const LightGeomT<V> (&hoisted)[N], Gout gout, IntSink int_sink, V (&d_albedo)[3][N],
                               V (&d_normal)[3][N], V (&d_rough)[N], V (&d_met)[3][N], Fetch fetch = Fetch(),
-                              GeomCache<V> gc = GeomCache<V>(), GeomSink geom_sink = GeomSink()) {
+                              GeomCache<V> gc = GeomCache<V>(), GeomSink geom_sink = GeomSink(),
+                              SavedOut saved_out = SavedOut()) {
   constexpr bool kGeom = GeomSink::kOn;
   static_assert(!kGeom || kLight == kLightDirectional || kLight == kLightPoint,
                 "geometry gradients run on the uncached per-texel light modes");
@@ -267,7 +295,17 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
   const bool two_pass = (!F.per_light) && L > 1;
   V g_tot[3][N];  // two-pass only: gradient w.r.t. every per-light colour
   fetch(0);
-  if (two_pass) {
+  if (two_pass && saved_out.have()) {
+    // single pass: gate and slope of encode(clamp(sum)) from the forward launch's output
+    V outv[3][N];
+    saved_out(outv);
+    fetch(L);
+    gout(0, outv, g_tot);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < N; ++i) g_tot[c][i] *= encode_slope_from_out(outv[c][i], F.return_srgb);
+  } else if (two_pass) {
     // pass 1: the accumulated image, to know where clamp(sum) gates and the slope of the encode
     V acc[3][N];
 #pragma unroll

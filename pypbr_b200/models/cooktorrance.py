@@ -30,6 +30,7 @@ from ..materials import MaterialBase
 
 # A/B switch for tests and tuning: True routes every call to the generic kernels (PbrCtDesc.force_generic).
 FORCE_GENERIC = False
+NO_SAVED_OUT = False   # tests: make the accumulate-mode backward recompute the summed image (two passes) as the C ABI does without fwd_out
 
 
 class BRDFModel(nn.Module, ABC):
@@ -116,13 +117,17 @@ class _CookTorranceFn(torch.autograd.Function):
         ctx.has_normal = normal is not None
         # the shared parameters may live on another device than the maps (the reference moves them with .to(device))
         ctx.leaf_meta = [(t.device, tuple(t.shape)) if t is not None else None for t in (intensity_leaf, lights_leaf, view_leaf)]
-        ctx.save_for_backward(albedo, normal if normal is not None else albedo.new_empty(0), roughness, metspec)
+        # accumulate mode with several lights: the output (which the caller holds anyway) lets the backward skip its
+        # first pass, the recomputation of the summed image (PbrCtGrads.fwd_out)
+        ctx.keep_out = cfg.L > 1 and not cfg.per_light
+        ctx.save_for_backward(albedo, normal if normal is not None else albedo.new_empty(0), roughness, metspec,
+                              out if ctx.keep_out else albedo.new_empty(0))
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         cfg = ctx.cfg
-        albedo, normal, roughness, metspec = ctx.saved_tensors
+        albedo, normal, roughness, metspec, fwd_out = ctx.saved_tensors
         if not ctx.has_normal:
             normal = None
         lib = _cabi.load()
@@ -131,6 +136,8 @@ class _CookTorranceFn(torch.autograd.Function):
         grad_out = grad_out.contiguous()
         g = _cabi.PbrCtGrads()
         g.grad_out, g.grad_out_sl = _out_plane(grad_out, cfg.per_light, cfg.batched)
+        if ctx.keep_out and not NO_SAVED_OUT:
+            g.fwd_out = _out_plane(fwd_out, False, cfg.batched)[0]
         need = ctx.needs_input_grad  # (cfg, albedo, normal, roughness, metspec, intensity, lights, view)
         dev = albedo.device
         d_albedo = torch.empty(albedo.shape, dtype=torch.float32, device=dev) if need[1] else None

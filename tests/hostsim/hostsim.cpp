@@ -26,6 +26,14 @@ struct HostGeomSink {
   void view(const float (&g)[3]) const { for (int c = 0; c < 3; ++c) d_geo[3 * L + c] += g[c]; }
 };
 
+template <class V>
+struct HostSavedOut {
+  bool on;
+  V out[3];
+  bool have() const { return on; }
+  void operator()(V (&o)[3][1]) const { for (int c = 0; c < 3; ++c) o[c][0] = out[c]; }
+};
+
 // kLightPointCached: what the kernels' prologue does per texel pair, with a private cache
 template <int LIGHT, class V>
 GeomCache<V> fill_cache(const CtStage& S, int L, V x, float y, V* store) {
@@ -81,7 +89,7 @@ template <int WF, bool HASN, int LIGHT, class V>
 void bwd_impl(const Dims& d, const CtStage& S, const CtFlags& F, const float* albedo, const float* normal,
               const float* rough, const float* metspec, const float* grad_out, const float* target,
               float loss_scale, double* loss_sum, float* d_albedo, float* d_normal, float* d_rough, float* d_met,
-              double* d_int, double* d_geo = nullptr) {
+              double* d_int, double* d_geo = nullptr, bool use_saved_out = false) {
   constexpr int NL = Lanes<V>::n;
   const int mc = WF == 0 ? 1 : 3;  // WF 2: metallic with 3 channels
   const int64_t HW = (int64_t)d.H * d.W;
@@ -126,17 +134,24 @@ void bwd_impl(const Dims& d, const CtStage& S, const CtFlags& F, const float* al
         if (LIGHT == kLightPointHoisted)
           point_light_geom(S.light[0].p[0], S.light[0].p[1], S.light[0].p[2], x[0], y, S.vx, S.vy, S.vz, hg[0]);
         V store[PBR_MAX_LIGHTS * 8];
+        // accumulate mode, L > 1, "saved forward output" flavour: what the forward launch wrote for these texels
+        HostSavedOut<V> saved{false, {}};
+        if (use_saved_out && !F.per_light && d.L > 1) {
+          auto keep = [&](int, const V(&v)[3][1]) { for (int c = 0; c < 3; ++c) saved.out[c] = v[c][0]; };
+          ct_forward_group<WF, LIGHT, V, 1>(S, F, a, n, r, m, x, y, hg, keep, fill_cache<LIGHT, V>(S, d.L, x[0], y, store));
+          saved.on = true;
+        }
         bool done = false;
         if constexpr (LIGHT == kLightDirectional || LIGHT == kLightPoint) {
           if (d_geo) {   // gradients of the light positions / directions and of the view direction
             ct_backward_group<WF, LIGHT, V, 1>(S, F, a, n, r, m, x, y, hg, gout, sink, da, dn, dr, dm, NoFetch(),
-                                               GeomCache<V>(), HostGeomSink{d_geo, d.L});
+                                               GeomCache<V>(), HostGeomSink{d_geo, d.L}, saved);
             done = true;
           }
         }
         if (!done)
           ct_backward_group<WF, LIGHT, V, 1>(S, F, a, n, r, m, x, y, hg, gout, sink, da, dn, dr, dm, NoFetch(),
-                                             fill_cache<LIGHT, V>(S, d.L, x[0], y, store));
+                                             fill_cache<LIGHT, V>(S, d.L, x[0], y, store), NoGeomSink(), saved);
         for (int k = 0; k < live; ++k) {
           for (int c = 0; c < 3; ++c) d_albedo[(b * 3 + c) * HW + o[k]] = lane_get(da[c][0], k);
           if (HASN && d_normal)
@@ -214,8 +229,9 @@ int hs_ct_backward(int B, int H, int W, int L, int workflow, int light_type, int
   static CtStage S;
   make_stage(d, light_type, light_size, view, lights, inten, S);
   CtFlags F{L, light_type == 1, albedo_is_srgb != 0, specular_is_srgb != 0, return_srgb != 0, per_light != 0};
+  // bit 4 of force_generic: accumulate-mode backward in one pass from the saved forward output (PbrCtGrads.fwd_out)
   DISPATCH(bwd_impl, d, S, F, albedo, normal, rough, metspec, grad_out, target, loss_scale, loss_sum, d_albedo,
-           d_normal, d_rough, d_met, d_int);
+           d_normal, d_rough, d_met, d_int, nullptr, (force_generic & 16) != 0);
   return 0;
 }
 

@@ -864,3 +864,41 @@ def test_height_normal_round_trip_matches_reference_fixture():
         compute_height_from_normal(None)
     with pytest.raises(ValueError):
         compute_height_from_normal(torch.zeros(2, 4, 4, device=DEV))
+
+
+@pytest.mark.parametrize("B,L,wf,light_type", [(3, 5, "metallic", "point"), (18, 3, "specular", "point"), (2, 4, "metallic", "directional")])
+def test_accumulate_backward_one_pass_from_saved_output_and_two_pass(B, L, wf, light_type, ct_path):
+    """Accumulate mode, L > 1: autograd hands the forward output to the backward (PbrCtGrads.fwd_out), which then skips the
+    recomputation of the summed image; without it (plain C-ABI callers) the kernel runs two passes.  Both against the oracle."""
+    from oracle import pbr_oracle as O
+    from pypbr_b200.models import cooktorrance as ct
+
+    maps, lights, inten, g = _random_case(900 + L, B, 22, 36, L, workflow=wf)
+    inten = inten * 40.0   # some texels saturate: the clamp of the sum gates
+    view = torch.tensor([0.0, 0.1, 1.0])
+    p = dict(light_type=light_type)
+    size = 1.0 if light_type == "point" else None
+    leaves = {k: t.clone().requires_grad_(True) for k, t in maps.items()}
+    ref = O.render(leaves, view, lights, inten, size, light_type, accumulate=True)
+    go = torch.rand(ref.shape, generator=g)
+    ref.backward(go)
+    assert float((ref.detach() >= 0.9999999).float().mean()) > 0.01   # the case does exercise the saturated gate (encode(1) = 0.99999994)
+    got = {}
+    for two_pass in (False, True):
+        ct.NO_SAVED_OUT = two_pass
+        try:
+            mat, lv = _material(maps, p, requires_grad=True)
+            out = _brdf(p, False)(mat, view, lights, inten, size, True)
+            out.backward(go.to(DEV))
+        finally:
+            ct.NO_SAVED_OUT = False
+        ratio, ok = fwd_ok(out.detach().cpu().numpy(), ref.detach().numpy())
+        assert ok, ratio
+        for k in maps:
+            ratio, ok = grad_ok(lv[k].grad.cpu().numpy(), leaves[k].grad.numpy())
+            assert ok, (k, two_pass, ratio)
+        got[two_pass] = {k: lv[k].grad for k in maps}
+    for k in maps:
+        a, b = got[False][k], got[True][k]
+        bad = (a - b).abs() > 4e-6 * (b.abs() + b.abs().mean())
+        assert float(bad.float().mean()) < 1e-3, k

@@ -32,7 +32,7 @@ def test_struct_layouts_match_header_sizes():
     # sizes the C compiler produces for the same declarations (LP64): catches field-order drift
     assert ctypes.sizeof(_cabi.PbrPlane) == 32
     assert ctypes.sizeof(_cabi.PbrCtDesc) == 12 * 4 + 4 * 32 + 8 + 3 * 8 + 32 + 8 + 8
-    assert ctypes.sizeof(_cabi.PbrCtGrads) == 32 + 8 + 4 * 32 + 3 * 8
+    assert ctypes.sizeof(_cabi.PbrCtGrads) == 32 + 8 + 4 * 32 + 3 * 8 + 32
     assert ctypes.sizeof(_cabi.PbrCtAdam) == 8 * 32 + 6 * 4 + 4 + 4  # trailing pad to 8
     assert ctypes.sizeof(_cabi.PbrBlendMap) == 3 * 32 + 8
     # ... and against the sizes the library itself reports (pbr_sizeof), for every descriptor

@@ -50,7 +50,7 @@ def test_forward_matches_golden(hostsim, name, generic):
     assert e_us <= 2 * e_ref + 1e-6
 
 
-@pytest.mark.parametrize("generic", [0, 1, 2, 3, 5, 7, 15])  # bit 0: generic light mode, bit 1: two texels per call (f2 lanes), bit 2: geometry cache for L > 1, bit 3: all 8 fields cached
+@pytest.mark.parametrize("generic", [0, 1, 2, 3, 5, 7, 15, 17, 23])  # bit 0: generic light mode, bit 1: two texels per call (f2 lanes), bit 2: geometry cache for L > 1, bit 3: all 8 fields cached, bit 4: one-pass accumulate backward from the saved forward output
 @pytest.mark.parametrize("name", golden_ct_cases())
 def test_backward_matches_golden(hostsim, name, generic):
     z = load_golden(name)
@@ -295,3 +295,38 @@ def test_light_and_view_gradients_match_reference_fixture(hostsim, tag):
             assert np.all(np.abs(got - want) <= tol), (name, got, want)
             # the reference's own fp32 run is further from fp64 than that or in the same ballpark
             assert np.all(np.abs(got - want) <= 4 * np.abs(z[f"{tag}_g32_{key}"] - want) + tol)
+
+
+@pytest.mark.parametrize("flags", [1, 3, 17, 19, 23])
+def test_saturated_accumulate_backward_one_and_two_pass(hostsim, flags):
+    """Strong lights: clamp(sum over lights) gates.  Two-pass backward (bit 4 clear) and the one-pass flavour that reads the
+    gate and the encode slope off the saved forward output (bit 4 set; encode(1) is 0.99999994 in fp32, in the reference too)."""
+    from oracle import pbr_oracle as O
+
+    gen = torch.Generator().manual_seed(77)
+    B, H, W, L = 2, 18, 26, 4
+    maps = {"albedo": torch.rand(B, 3, H, W, generator=gen), "roughness": torch.rand(B, 1, H, W, generator=gen) * 0.8 + 0.2,
+            "metallic": torch.rand(B, 1, H, W, generator=gen)}
+    n = torch.randn(B, 3, H, W, generator=gen) * torch.tensor([0.3, 0.3, 0.0]).view(1, 3, 1, 1) + torch.tensor([0.0, 0.0, 1.0]).view(1, 3, 1, 1)
+    maps["normal"] = torch.nn.functional.normalize(n, dim=1)
+    ang = torch.arange(L, dtype=torch.float32) * (6.2831853 / L)
+    lights = torch.stack([0.4 * torch.cos(ang), 0.4 * torch.sin(ang), torch.ones(L)], dim=1)
+    inten = torch.ones(L, 3) * 8.0
+    view = torch.tensor([0.0, 0.0, 1.0])
+    leaves = {k: t.clone().requires_grad_(True) for k, t in maps.items()}
+    out = O.render(leaves, view, lights, inten, 1.0, "point", accumulate=True)
+    assert float((out.detach() >= 0.9999999).float().mean()) > 0.01
+    go = torch.rand(out.shape, generator=gen)
+    out.backward(go)
+    a = {k: np.ascontiguousarray(t.numpy()) for k, t in maps.items()}
+    vn, ln, inn, gon = (np.ascontiguousarray(t.numpy()) for t in (view, lights, inten, go))
+    args = (B, H, W, L, 0, 1, 1, 1, 1, 0, ctypes.c_float(1.0), fp(a["albedo"]), fp(a["normal"]), fp(a["roughness"]),
+            fp(a["metallic"]), fp(vn), fp(ln), fp(inn))
+    da = np.zeros_like(a["albedo"]); dn = np.zeros_like(a["albedo"]); dr = np.zeros_like(a["roughness"]); dm = np.zeros_like(a["metallic"])
+    di = np.zeros((L, 3), np.float64)
+    loss = ctypes.c_double(0)
+    assert hostsim.hs_ct_backward(*args, fp(gon), None, ctypes.c_float(0), ctypes.byref(loss), fp(da), fp(dn), fp(dr), fp(dm),
+                                  di.ctypes.data_as(D), flags) == 0
+    for k, g in (("albedo", da), ("normal", dn), ("roughness", dr), ("metallic", dm)):
+        ratio, ok = grad_ok(g, leaves[k].grad.numpy())
+        assert ok, f"d_{k}: {ratio}"
