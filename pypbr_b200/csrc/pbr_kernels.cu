@@ -348,6 +348,15 @@ __global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kerne
   }
 }
 
+#ifndef PBR_COLD_UNROLL
+#define PBR_COLD_UNROLL 4   // measured: branching over the cold path (1) is not faster than predicating it
+#endif
+#ifndef PBR_PACKED_LOSS
+#define PBR_PACKED_LOSS 1
+#endif
+constexpr int kColdUnroll = PBR_COLD_UNROLL;
+constexpr bool kPackedLoss = PBR_PACKED_LOSS != 0;
+
 // per-thread asynchronous copies global -> shared (LDGSTS) for the backward kernel's grad_out / target ring
 constexpr int kRing = 4;
 __device__ __forceinline__ void cp_async8(float* dst_smem, const float* src) {
@@ -378,18 +387,21 @@ __device__ __forceinline__ float warp_sum(float v) {
 #endif
 constexpr int bwd_min_ctas(int light_mode) { return light_mode == kLightPointCached ? PBR_BWD_CACHED_MIN_CTAS : PBR_BWD_MIN_CTAS; }
 
-// The saved forward output of the material / row segment being back-propagated (PbrCtGrads.fwd_out).
+// The saved forward output of the row segment being back-propagated (PbrCtGrads.fwd_out).  It travels through slot 1 of
+// the thread's cp.async ring (accumulate mode keeps only slot 0 busy, with grad_out), requested together with grad_out
+// before the per-texel setup, so its latency is hidden like grad_out's.
 struct CtaSavedOut {
-  const CtKParams& p;
-  const Where& w;
-  int b, s, vs;
-  __device__ __forceinline__ bool have() const { return p.fout.ptr != nullptr; }
+  const float* slot1;   // this thread's column of ring slot 1: [channel][thread][NT]
+  bool on;
+  __device__ __forceinline__ bool have() const { return on; }
   template <int G>
   __device__ __forceinline__ void operator()(V (&o)[3][G]) const {
+    cp_async_wait<0>();
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float tv[kLanes * G];
-      load_seg<kLanes * G>(p.fout.ptr + plane_off(p.fout, b, c, w.row, w.col0 + kLanes * s), w.vec, vs, tv);
+#pragma unroll
+      for (int i = 0; i < kLanes * G; ++i) tv[i] = slot1[c * (kCtThreads * kLanes * G) + i];
       pairs_of<G>(tv, 0, o[c]);
     }
   }
@@ -445,6 +457,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
   float* const s_adam = reinterpret_cast<float*>(s_dyn + p.adam_smem_off) + tid * kCtTexels;
 
   float loss_local = 0.0f;
+  V loss_v = splat<V>(0.0f);   // squared error of the vector path, one partial sum per lane
   const int b0 = blockIdx.z * p.mats_per_cta;
   const int b1 = min(b0 + p.mats_per_cta, p.B);
   for (int b = b0; b < b1; ++b) {
@@ -466,7 +479,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
           if (kCtTexels == 2 && w.vec) {
             cp_async8(dst, src[j]);
           } else {
-#pragma unroll
+#pragma unroll kColdUnroll   // cold path, branched over
             for (int i = 0; i < kCtTexels; ++i) cp_async4(dst + i, src[j] + (i < w.valid ? i : (w.valid > 0 ? w.valid - 1 : 0)));
           }
         }
@@ -503,17 +516,21 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       float* ring = s_ring + tid * NT;   // [slot][channel][thread][NT]
       const int nl_src = p.flags.per_light ? p.flags.L : 1;
       const float* const gbase = p.gsrc.ptr + plane_off(p.gsrc, b, 0, w.row, w.col0 + kLanes * s);   // once per material
+      const bool have_fout = p.fout.ptr != nullptr;   // accumulate mode only (nl_src == 1): slot 1 carries the saved forward output
+      const float* const fbase = have_fout ? p.fout.ptr + plane_off(p.fout, b, 0, w.row, w.col0 + kLanes * s) : nullptr;
       auto issue = [&](int l) {
-        if (l < nl_src) {
-          const float* const gl = gbase + (int64_t)l * p.gsrc_sl;
+        const bool saved = have_fout && l == 1;
+        if (l < nl_src || saved) {
+          const float* const gl = saved ? fbase : gbase + (int64_t)l * p.gsrc_sl;
+          const int64_t csc = saved ? p.fout.sc : p.gsrc.sc;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float* src = gl + (int64_t)c * p.gsrc.sc;
+            const float* src = gl + (int64_t)c * csc;
             float* dst = ring + ((l % kRing) * 3 + c) * (kCtThreads * NT);
             if (NT == 2 && w.vec) {
               cp_async8(dst, src);
             } else {
-#pragma unroll
+#pragma unroll kColdUnroll   // cold path (ragged or unaligned rows): a real loop is branched over instead of predicated
               for (int i = 0; i < NT; ++i) cp_async4(dst + i, src + (i < vs ? i : (vs > 0 ? vs - 1 : 0)));
             }
           }
@@ -538,6 +555,24 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       };
       auto gout = [&](int l, const V(&outv)[3][G], V(&g)[3][G]) {
         take(l);
+        if (kPackedLoss && w.vec) {   // every lane is a live texel (uniform over the grid): packed arithmetic, no masks
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            V t[G];
+            pairs_of<G>(t_cur[c], 0, t);
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+              if (is_loss) {
+                const V diff = outv[c][i] - t[i];
+                loss_v += diff * diff;
+                g[c][i] = diff * (2.0f * p.loss_scale);
+              } else {
+                g[c][i] = t[i];
+              }
+            }
+          }
+          return;
+        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           float ov[kLanes * G], gv[kLanes * G];
@@ -569,10 +604,10 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       gcs.base += s * gc.stride;
       if constexpr (kGeom) {
         ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs,
-                                            CtaGeomSink{s_geo, p.flags.L, tid, live}, CtaSavedOut{p, w, b, s, vs});
+                                            CtaGeomSink{s_geo, p.flags.L, tid, live}, CtaSavedOut{ring + 3 * (kCtThreads * NT), have_fout});
       } else {
         ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs,
-                                            NoGeomSink(), CtaSavedOut{p, w, b, s, vs});
+                                            NoGeomSink(), CtaSavedOut{ring + 3 * (kCtThreads * NT), have_fout});
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) { unpair_to<G>(da[c], s, d_albedo[c]); unpair_to<G>(dn[c], s, d_normal[c]); unpair_to<G>(dm[c], s, d_met[c]); }
@@ -661,6 +696,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
   }
 
   if (is_loss) {
+    loss_local += lane_sum(loss_v);
     float sum = warp_sum(loss_local * live);
     if ((tid & 31) == 0) s_loss[tid >> 5] = sum;
   }
