@@ -58,6 +58,33 @@ def test_argument_errors_come_back_as_codes_without_touching_the_gpu():
     b = _cabi.PbrBlendDesc()
     b.B, b.H, b.W, b.n_maps = 1, 4, 4, 13
     assert lib.pbr_blend(ctypes.byref(b), None) == -4
+    # the one-launch fit step: descriptors are validated in the same order, and batch-broadcast maps (sb == 0) are
+    # refused because they would be updated in place by every material
+    assert lib.pbr_ct_fit_step(None, None, None, None, None) == -1
+    fake = 0x1000   # never dereferenced: argument checks only
+    d = _cabi.PbrCtDesc()
+    d.B, d.H, d.W, d.L = 2, 4, 4, 1
+    for pl in ("albedo", "roughness", "metspec"):
+        setattr(d, pl, _cabi.PbrPlane(fake, 0, 16, 4))
+    hv = (ctypes.c_float * 3)(0, 0, 1)
+    d.view = d.lights = d.intensity = ctypes.cast(hv, ctypes.c_void_p)
+    ls = _cabi.PbrCtLoss()
+    assert lib.pbr_ct_fit_step(ctypes.byref(d), ctypes.byref(ls), None, None, None) == -1      # no target / Adam state
+    ls.target, ls.loss_sum = _cabi.PbrPlane(fake, 48, 16, 4), fake
+    a = _cabi.PbrCtAdam()
+    assert lib.pbr_ct_fit_step(ctypes.byref(d), ctypes.byref(ls), ctypes.byref(a), None, None) == -2   # broadcast maps
+    for pl in ("albedo", "roughness", "metspec"):
+        setattr(d, pl, _cabi.PbrPlane(fake, 48, 16, 4))
+    assert lib.pbr_ct_fit_step(ctypes.byref(d), ctypes.byref(ls), ctypes.byref(a), None, None) == -1   # moments are NULL
+    # normal utilities
+    n = _cabi.PbrNormalOpDesc()
+    assert lib.pbr_normal_op(None, None) == -1
+    n.B, n.H, n.W, n.op = 1, 4, 4, 9
+    assert lib.pbr_normal_op(ctypes.byref(n), None) == -3
+    n.op = _cabi.NORMAL_OP_FROM_HEIGHT
+    assert lib.pbr_normal_op(ctypes.byref(n), None) == -1
+    n.in_ = n.out = _cabi.PbrPlane(fake, 0, 16, 4)
+    assert lib.pbr_normal_op(ctypes.byref(n), None) == -1    # a stencil cannot run in place
 
 
 # ------------------------------------------------------------------ material container
