@@ -126,6 +126,8 @@ def _random_case(seed, B, H, W, L, workflow="metallic", rough_lo=0.2, normal=Tru
     (19, 9, 40, 6, False, "metallic"),    # geometry cache (l, h cached): B > one CTA's walk, per-light outputs
     (18, 8, 33, 3, True, "specular"),     # geometry cache (all 8 fields): two-pass accumulate backward, ragged W
     (17, 4, 24, 12, True, "metallic"),    # geometry cache at 12 lights
+    (3, 6, 24, 20, True, "metallic"),     # more lights than the cache takes: per-texel geometry, one material per CTA
+    (2, 5, 20, 18, False, "specular"),    # ... per-light outputs
 ])
 def test_against_oracle_seeded(B, H, W, L, acc, wf, ct_path):
     """Fresh seeded inputs (not in the fixtures) against the oracle run on the host."""

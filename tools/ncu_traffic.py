@@ -16,7 +16,12 @@ for arg in sys.argv[1:]:
         rd = float(r[col["dram__bytes_read.sum"]]) * UNIT[units[col["dram__bytes_read.sum"]]]
         wr = float(r[col["dram__bytes_write.sum"]]) * UNIT[units[col["dram__bytes_write.sum"]]]
         kind = "backward" if "backward" in name else ("forward" if "forward" in name else name.split("(")[0].replace("void ", ""))
+        def num(metric):
+            return float(r[col[metric]]) if metric in col and r[col[metric]] not in ("", "n/a") else None
         out[f"{cfg}:{kind}"] = {"kernel": name, "bytes": rd + wr, "read": rd, "write": wr,
+                                "fma_pipe_busy_pct": num("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                                "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                                "warp_instructions": num("smsp__inst_executed.sum"),
                                 "source": f"ncu --set full, {os.path.basename(path)} (profiles/)"}
 json.dump(out, open(out_path, "w"), indent=1)
 print(json.dumps(out, indent=1))
