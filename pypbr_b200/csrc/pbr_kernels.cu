@@ -236,6 +236,28 @@ __device__ __forceinline__ void load_material(const CtKParams& p, const Where& w
   }
 }
 
+// The maps of the NEXT material of the walk are pulled into L2 while the current one is shaded (one request per 128-byte
+// line: a warp's row segment of a plane is 256 bytes), so the loads at the top of the next iteration hit L2 instead of
+// waiting for HBM.  No registers, no shared memory (the multi-light kernels have neither to spare).
+#ifndef PBR_PREFETCH_NEXT
+#define PBR_PREFETCH_NEXT 1
+#endif
+__device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int WF>
+__device__ __forceinline__ void prefetch_material(const CtKParams& p, const Where& w, int b) {
+  if (!PBR_PREFETCH_NEXT || ((threadIdx.x * kCtTexels) & 31) != 0) return;   // first thread of every 128-byte line
+#pragma unroll
+  for (int c = 0; c < 3; ++c) prefetch_l2(p.albedo.ptr + plane_off(p.albedo, b, c, w.row, w.col0));
+  if (p.normal.ptr) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) prefetch_l2(p.normal.ptr + plane_off(p.normal, b, c, w.row, w.col0));
+  }
+  prefetch_l2(p.roughness.ptr + plane_off(p.roughness, b, 0, w.row, w.col0));
+#pragma unroll
+  for (int c = 0; c < (WF == 0 ? 1 : 3); ++c) prefetch_l2(p.metspec.ptr + plane_off(p.metspec, b, c, w.row, w.col0));
+}
+
 // texels [kLanes*s0, kLanes*(s0+G)) of a thread's row segment as G lane-values
 template <int G, int N>
 __device__ __forceinline__ void pairs_of(const float (&src)[N], int s0, V (&dst)[G]) {
@@ -312,6 +334,7 @@ __global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kerne
   for (int b = b0; b < b1; ++b) {
     float araw[3][kCtTexels], nraw[3][kCtTexels], rough[kCtTexels], mraw[3][kCtTexels];
     load_material<WF>(p, w, b, araw, nraw, rough, mraw);
+    if (b + 1 < b1) prefetch_material<WF>(p, w, b + 1);
     float outv[3][kCtTexels];
 #pragma unroll
     for (int s = 0; s < kSlots; s += G) {
@@ -463,6 +486,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
   for (int b = b0; b < b1; ++b) {
     float araw[3][kCtTexels], nraw[3][kCtTexels], rough[kCtTexels], mraw[3][kCtTexels];
     load_material<WF>(p, w, b, araw, nraw, rough, mraw);
+    if (b + 1 < b1) prefetch_material<WF>(p, w, b + 1);
     if (p.adam_on) {
       // Fused fit step: what the Adam epilogue of THIS material needs (parameters and both moments of every channel)
       // starts travelling now, as per-thread cp.async copies into shared memory, and lands while the light loop runs.

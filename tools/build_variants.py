@@ -28,6 +28,7 @@ VARIANTS = {
     # geometry cache of the multi-light kernels (point lights, L > 1): off / backward register budget / light-loop unrolling
     "gc_off": ["-DPBR_GC_MAX_BYTES=0"],
     "gc_b3": v(bwd_cached_min_ctas=3),
+    "x_nopf": v(prefetch_next=0),
     "x_cold1": v(cold_unroll=1),
     "x_pl0": v(packed_loss=0),
     "u_f2": v(fwd_unroll=2),
