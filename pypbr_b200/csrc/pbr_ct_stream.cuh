@@ -57,6 +57,26 @@ constexpr int kST = PBR_STREAM_TEXELS;
 static_assert((kST == 2 || kST == 4) && kST % kLanes == 0, "stream kernels: 2 or 4 texels per thread");
 constexpr int kSSlots = kST / kLanes;               // lane-values per thread
 constexpr int kTileFloats = kStreamThreads * kST;   // floats of one plane in one stage (2 KB at 128 threads x 4 texels)
+// PBR_STREAM_PER_WARP: every warp runs its OWN copy pipeline over its own 32 x kST texels of a tile row (plane stride
+// inside a stage = one warp segment) instead of warp 0 feeding the whole CTA: a warp refills a stage right after its own
+// last read of it, without waiting for the other warps or for its own arithmetic.
+// Measured (C2 shape, tools/tune.py): forward 0.499 -> 0.474 ms (95 % of the HBM copy peak); the backward, whose refill
+// point sits between the two pairs it shades one after the other, is 1.5 % slower that way (0.944 -> 0.959 ms) and keeps
+// the CTA-level pipeline.  Deeper pipelines (3, 4 stages) are slower in both.
+#ifndef PBR_STREAM_PER_WARP_FWD
+#define PBR_STREAM_PER_WARP_FWD 1
+#endif
+#ifndef PBR_STREAM_PER_WARP_BWD
+#define PBR_STREAM_PER_WARP_BWD 0
+#endif
+#ifndef PBR_STREAM_BWD_LATE_REFILL
+#define PBR_STREAM_BWD_LATE_REFILL 0   // per-warp backward: refill after the whole tile instead of after the last read
+#endif
+constexpr bool kPerWarpFwd = PBR_STREAM_PER_WARP_FWD != 0, kPerWarpBwd = PBR_STREAM_PER_WARP_BWD != 0;
+constexpr bool kLateRefill = PBR_STREAM_BWD_LATE_REFILL != 0;
+constexpr int kWarpSeg = 32 * kST;                                  // floats of one plane a warp owns per tile row
+constexpr int kMaxPipes = kStreamThreads / 32;                      // independent copy pipelines per CTA (per-warp mode)
+PBR_HDC int plane_stride(bool per_warp) { return per_warp ? kWarpSeg : kStreamThreads * kST; }   // floats between two planes of a stage
 constexpr int kMaxSrcPlanes = 13;                   // albedo 3 + roughness 1 + metallic|specular 3 + normal 3 + grad_out|target 3
 
 // backward flavours (compile-time, so the plain backward carries no reduction code)
@@ -71,7 +91,7 @@ struct StreamSrc {
 };
 
 struct StreamShared {
-  uint64_t full[kStages];    // producer -> consumers: the copies of the stage have landed (transaction bytes)
+  uint64_t full[kStages * kMaxPipes];   // producer -> consumers: the copies of the stage have landed (transaction bytes)
   uint64_t empty[kStages];   // consumers -> producer: one arrival per warp after its last read of the stage
   StreamSrc src[kMaxSrcPlanes];
   int n_src;
@@ -124,6 +144,21 @@ __device__ __forceinline__ void stream_issue(const StreamShared& sh, uint64_t* b
   }
 }
 
+// per-warp pipeline: the calling warp enqueues ITS segment (32 x kST texels of its row) of every plane of material `b`
+__device__ __forceinline__ void warp_issue(const StreamShared& sh, uint64_t* bar, float* stage, int b, int64_t row_in_tile,
+                                           int col_in_tile, int seg_bytes, uint64_t policy) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(sh.n_src * seg_bytes));
+  __syncwarp();
+  if (lane < sh.n_src) {
+    const StreamSrc& s = sh.src[lane];
+    bulk_g2s(stage + s.slot * kWarpSeg, s.base + (int64_t)b * s.sb + row_in_tile * s.sh + col_in_tile, (uint32_t)seg_bytes, bar,
+             policy);
+  }
+}
+// orders this thread's earlier shared-memory reads before copies the async proxy performs later
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // one lane-value (kLanes consecutive floats) from shared memory / to global memory
 __device__ __forceinline__ V lds_v(const float* p) {
 #if defined(PBR_SCALAR_LANES)
@@ -148,8 +183,10 @@ struct StreamWhere {
   int slot_stride;      // texels between a thread's consecutive slots (= blockDim.x * kLanes)
   int toff;             // offset of slot 0 inside a tile plane (floats)
   int rows_valid, seg_bytes, row_floats;
+  int wcol;             // per-warp pipelines: offset of the warp's segment inside the tile row
   bool row_ok;
 };
+template <bool kPerWarp>
 __device__ __forceinline__ StreamWhere stream_locate(int H, int W) {
   StreamWhere w;
   w.row_floats = blockDim.x * kST;
@@ -162,6 +199,15 @@ __device__ __forceinline__ StreamWhere stream_locate(int H, int W) {
   w.rows_valid = min((int)blockDim.y, H - w.row0);
   w.seg_bytes = min(w.row_floats, W - w.col0) * 4;
   w.row_ok = w.row < H;
+  if (kPerWarp) {   // blockDim.x is a multiple of 32: a warp sits inside one tile row and owns kWarpSeg contiguous texels of it
+    const int lane = threadIdx.x & 31;
+    w.wcol = (threadIdx.x >> 5) * kWarpSeg;           // first texel of the warp's segment inside the tile row
+    w.slot_stride = 32 * kLanes;
+    w.col = w.col0 + w.wcol + lane * kLanes;
+    w.toff = lane * kLanes;
+    const int left = W - (w.col0 + w.wcol);
+    w.seg_bytes = (w.row_ok && left > 0) ? min(kWarpSeg, left) * 4 : 0;   // 0: the warp has nothing to copy or shade
+  }
   return w;
 }
 // W % 4 == 0 (and kLanes <= 2): a slot's texels are all inside or all outside the image
@@ -193,15 +239,19 @@ template <int WF, int kLight>
 __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_FWD_MIN_CTAS) ct_forward_stream(const __grid_constant__ CtKParams p) {
   using SL = Slots<WF, false>;
   constexpr int G = kSSlots;   // all of the thread's pairs are shaded together
+  constexpr bool kPerWarp = kPerWarpFwd;
+  constexpr int kPlaneStride = plane_stride(kPerWarp), kPipes = kPerWarp ? kMaxPipes : 1;
   extern __shared__ __align__(128) float stream_smem[];
   __shared__ CtStage S;
   __shared__ StreamShared sh;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const StreamWhere w = stream_locate(p.H, p.W);
+  const StreamWhere w = stream_locate<kPerWarp>(p.H, p.W);
   if (tid == 0) {
     stream_build_table<WF, false>(p, w.row0, w.col0, sh);
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], kStreamThreads / 32); }
+    for (int s = 0; s < kStages; ++s) mbar_init(&sh.empty[s], kStreamThreads / 32);
+#pragma unroll
+    for (int s = 0; s < kStages * kPipes; ++s) mbar_init(&sh.full[s], 1);
     mbar_init_fence();
   }
   stage_params(p, S);  // ends with __syncthreads()
@@ -210,7 +260,17 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_FWD_MIN_CTAS) ct_fo
   const int ntiles = min(b0 + p.mats_per_cta, p.B) - b0;
   const int stage_floats = (p.normal.ptr ? SL::count : SL::count_no_normal) * kTileFloats;
   uint64_t policy = 0;
-  if (tid < 32) {
+  // per-warp pipelines: this warp's barriers and stage buffers (planes x kWarpSeg floats per stage)
+  const int pipe = kPerWarp ? (tid >> 5) : 0;
+  uint64_t* const full = sh.full + pipe * kStages;
+  float* const my_stages = stream_smem + (kPerWarp ? pipe * kStages * (stage_floats / (kTileFloats / kWarpSeg)) : 0);
+  const int my_stage_floats = kPerWarp ? stage_floats / (kTileFloats / kWarpSeg) : stage_floats;
+  if (kPerWarp) {
+    policy = l2_evict_first_policy();
+    if (w.seg_bytes > 0)
+      for (int k = 0; k < kStages && k < ntiles; ++k)
+        warp_issue(sh, &full[k], my_stages + k * my_stage_floats, b0 + k, threadIdx.y, w.wcol, w.seg_bytes, policy);
+  } else if (tid < 32) {
     policy = l2_evict_first_policy();
     for (int k = 0; k < kStages && k < ntiles; ++k)
       stream_issue(sh, &sh.full[k], stream_smem + k * stage_floats, b0 + k, w.rows_valid, w.seg_bytes, w.row_floats, policy);
@@ -231,23 +291,31 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_FWD_MIN_CTAS) ct_fo
 
   for (int k = 0; k < ntiles; ++k) {
     const int s = k % kStages;
-    const float* st = stream_smem + s * stage_floats + w.toff;
-    mbar_wait(&sh.full[s], (k / kStages) & 1);
+    const float* st = my_stages + s * my_stage_floats + w.toff;
+    if (!kPerWarp || w.seg_bytes > 0) mbar_wait(&full[s], (k / kStages) & 1);
     V a[3][G], n[3][G], r[G], m[3][G];
 #pragma unroll
     for (int j = 0; j < G; ++j) {
       const float* sj = st + j * w.slot_stride;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) a[c][j] = lds_v(sj + (SL::albedo + c) * kTileFloats);
-      r[j] = lds_v(sj + SL::rough * kTileFloats);
+      for (int c = 0; c < 3; ++c) a[c][j] = lds_v(sj + (SL::albedo + c) * kPlaneStride);
+      r[j] = lds_v(sj + SL::rough * kPlaneStride);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) m[c][j] = c < SL::mc ? lds_v(sj + (SL::met + c) * kTileFloats) : splat<V>(0.0f);
+      for (int c = 0; c < 3; ++c) m[c][j] = c < SL::mc ? lds_v(sj + (SL::met + c) * kPlaneStride) : splat<V>(0.0f);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) n[c][j] = has_normal ? lds_v(sj + (SL::normal + c) * kTileFloats) : splat<V>(c == 2 ? 1.0f : 0.0f);
+      for (int c = 0; c < 3; ++c) n[c][j] = has_normal ? lds_v(sj + (SL::normal + c) * kPlaneStride) : splat<V>(c == 2 ? 1.0f : 0.0f);
     }
-    // this warp holds its texels in registers: tell the producer (no CTA-wide barrier - warps drift freely)
+    // this warp holds its texels in registers: refill its own stage (per-warp pipelines), or tell the producer
+    // (no CTA-wide barrier - warps drift freely)
     __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&sh.empty[s]);
+    if (kPerWarp) {
+      if (w.seg_bytes > 0 && k + kStages < ntiles) {
+        fence_proxy_async();
+        warp_issue(sh, &full[s], my_stages + s * my_stage_floats, b0 + k + kStages, threadIdx.y, w.wcol, w.seg_bytes, policy);
+      }
+    } else if ((tid & 31) == 0) {
+      mbar_arrive(&sh.empty[s]);
+    }
     if (any) {
       V outv[3][G];
       auto emit = [&](int, const V(&v)[3][G]) {
@@ -274,7 +342,7 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_FWD_MIN_CTAS) ct_fo
     }
     o += p.out.sb;
     // producer: by the time warp 0 has shaded tile k every warp has long since read stage s
-    if (tid < 32 && k + kStages < ntiles) {
+    if (!kPerWarp && tid < 32 && k + kStages < ntiles) {
       mbar_wait(&sh.empty[s], (k / kStages) & 1);
       stream_issue(sh, &sh.full[s], stream_smem + s * stage_floats, b0 + k + kStages, w.rows_valid, w.seg_bytes,
                    w.row_floats, policy);
@@ -288,6 +356,8 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_FWD_MIN_CTAS) ct_fo
 template <int WF, int kLight, int kMode>
 __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_backward_stream(const __grid_constant__ CtKParams p) {
   using SL = Slots<WF, true>;
+  constexpr bool kPerWarp = kPerWarpBwd;
+  constexpr int kPlaneStride = plane_stride(kPerWarp), kPipes = kPerWarp ? kMaxPipes : 1;
   constexpr bool kLoss = (kMode & kModeLoss) != 0;
   constexpr bool kIntGrad = (kMode & kModeIntGrad) != 0;
   extern __shared__ __align__(128) float stream_smem[];
@@ -295,11 +365,13 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_ba
   __shared__ StreamShared sh;
   __shared__ float s_red[kStreamThreads / 32][4];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const StreamWhere w = stream_locate(p.H, p.W);
+  const StreamWhere w = stream_locate<kPerWarp>(p.H, p.W);
   if (tid == 0) {
     stream_build_table<WF, true>(p, w.row0, w.col0, sh);
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], kStreamThreads / 32); }
+    for (int s = 0; s < kStages; ++s) mbar_init(&sh.empty[s], kStreamThreads / 32);
+#pragma unroll
+    for (int s = 0; s < kStages * kPipes; ++s) mbar_init(&sh.full[s], 1);
     mbar_init_fence();
   }
   stage_params(p, S);  // ends with __syncthreads()
@@ -308,7 +380,17 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_ba
   const int ntiles = min(b0 + p.mats_per_cta, p.B) - b0;
   const int stage_floats = (p.normal.ptr ? SL::count : SL::count_no_normal) * kTileFloats;
   uint64_t policy = 0;
-  if (tid < 32) {
+  // per-warp pipelines: this warp's barriers and stage buffers (planes x kWarpSeg floats per stage)
+  const int pipe = kPerWarp ? (tid >> 5) : 0;
+  uint64_t* const full = sh.full + pipe * kStages;
+  float* const my_stages = stream_smem + (kPerWarp ? pipe * kStages * (stage_floats / (kTileFloats / kWarpSeg)) : 0);
+  const int my_stage_floats = kPerWarp ? stage_floats / (kTileFloats / kWarpSeg) : stage_floats;
+  if (kPerWarp) {
+    policy = l2_evict_first_policy();
+    if (w.seg_bytes > 0)
+      for (int k = 0; k < kStages && k < ntiles; ++k)
+        warp_issue(sh, &full[k], my_stages + k * my_stage_floats, b0 + k, threadIdx.y, w.wcol, w.seg_bytes, policy);
+  } else if (tid < 32) {
     policy = l2_evict_first_policy();
     for (int k = 0; k < kStages && k < ntiles; ++k)
       stream_issue(sh, &sh.full[k], stream_smem + k * stage_floats, b0 + k, w.rows_valid, w.seg_bytes, w.row_floats, policy);
@@ -329,25 +411,33 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_ba
 
   for (int k = 0; k < ntiles; ++k) {
     const int s = k % kStages;
-    const float* st = stream_smem + s * stage_floats + w.toff;
-    mbar_wait(&sh.full[s], (k / kStages) & 1);
+    const float* st = my_stages + s * my_stage_floats + w.toff;
+    if (!kPerWarp || w.seg_bytes > 0) mbar_wait(&full[s], (k / kStages) & 1);
 #pragma unroll
     for (int j = 0; j < kSSlots; ++j) {
       const float* sj = st + j * w.slot_stride;
       V a[3][1], n[3][1], r[1], m[3][1], gs[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) a[c][0] = lds_v(sj + (SL::albedo + c) * kTileFloats);
-      r[0] = lds_v(sj + SL::rough * kTileFloats);
+      for (int c = 0; c < 3; ++c) a[c][0] = lds_v(sj + (SL::albedo + c) * kPlaneStride);
+      r[0] = lds_v(sj + SL::rough * kPlaneStride);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) m[c][0] = c < SL::mc ? lds_v(sj + (SL::met + c) * kTileFloats) : splat<V>(0.0f);
+      for (int c = 0; c < 3; ++c) m[c][0] = c < SL::mc ? lds_v(sj + (SL::met + c) * kPlaneStride) : splat<V>(0.0f);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) gs[c] = lds_v(sj + (SL::gsrc + c) * kTileFloats);   // grad_out, or the target image in loss mode
+      for (int c = 0; c < 3; ++c) gs[c] = lds_v(sj + (SL::gsrc + c) * kPlaneStride);   // grad_out, or the target image in loss mode
 #pragma unroll
-      for (int c = 0; c < 3; ++c) n[c][0] = has_normal ? lds_v(sj + (SL::normal + c) * kTileFloats) : splat<V>(c == 2 ? 1.0f : 0.0f);
+      for (int c = 0; c < 3; ++c) n[c][0] = has_normal ? lds_v(sj + (SL::normal + c) * kPlaneStride) : splat<V>(c == 2 ? 1.0f : 0.0f);
       if (j == kSSlots - 1) {
-        // last read of the stage by this warp: tell the producer (no CTA-wide barrier - warps drift freely)
+        // last read of the stage by this warp: refill it (per-warp pipelines) or tell the producer (no CTA-wide
+        // barrier - warps drift freely)
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&sh.empty[s]);
+        if (kPerWarp) {
+          if (!kLateRefill && w.seg_bytes > 0 && k + kStages < ntiles) {
+            fence_proxy_async();
+            warp_issue(sh, &full[s], my_stages + s * my_stage_floats, b0 + k + kStages, threadIdx.y, w.wcol, w.seg_bytes, policy);
+          }
+        } else if ((tid & 31) == 0) {
+          mbar_arrive(&sh.empty[s]);
+        }
       }
       if (slot_active(w, j, p.W)) {
         const V xs[1] = {x[j]};
@@ -395,12 +485,17 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_ba
         }
       }
     }
+    if (kPerWarp && kLateRefill && w.seg_bytes > 0 && k + kStages < ntiles) {
+      __syncwarp();
+      fence_proxy_async();
+      warp_issue(sh, &full[s], my_stages + s * my_stage_floats, b0 + k + kStages, threadIdx.y, w.wcol, w.seg_bytes, policy);
+    }
     if (o_a) o_a += p.d_albedo.sb;
     if (o_n) o_n += p.d_normal.sb;
     if (o_r) o_r += p.d_roughness.sb;
     if (o_m) o_m += p.d_metspec.sb;
     // producer: by the time warp 0 has shaded tile k every warp has long since read stage s
-    if (tid < 32 && k + kStages < ntiles) {
+    if (!kPerWarp && tid < 32 && k + kStages < ntiles) {
       mbar_wait(&sh.empty[s], (k / kStages) & 1);
       stream_issue(sh, &sh.full[s], stream_smem + s * stage_floats, b0 + k + kStages, w.rows_valid, w.seg_bytes,
                    w.row_floats, policy);

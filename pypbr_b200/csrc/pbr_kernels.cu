@@ -1146,10 +1146,14 @@ static bool fits_i32(const PbrPlane& pl, int H, int W) {
   return !pl.ptr || ((int64_t)(H - 1) * pl.sh + W) < (int64_t)INT32_MAX;
 }
 
-static bool stream_shape(const CtKParams& k, dim3& grid, dim3& block, int& mats) {
+static bool stream_shape(const CtKParams& k, dim3& grid, dim3& block, int& mats, bool per_warp) {
   if (stream_disabled() || k.force_generic || k.flags.L != 1 || !k.vec_ok || (k.W % 4) != 0) return false;
   static const int min_bx = [] { const char* e = getenv("PBR_STREAM_MIN_BX"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
   int groups = k.W / kST, bx = min_bx < 4 / kST ? 4 / kST : min_bx;   // a row segment is a multiple of 16 bytes
+  if (per_warp) {   // per-warp copy pipelines: a warp must sit inside one tile row
+    if (groups < 32) return false;   // narrower than one warp segment: the generic kernels take it
+    if (bx < 32) bx = 32;
+  }
   while (bx < groups && bx < kStreamThreads) bx <<= 1;
   int by = kStreamThreads / bx;
   int64_t gy = ((int64_t)k.H + by - 1) / by;
@@ -1203,7 +1207,7 @@ static void launch_bwd_stream(const CtKParams& k, dim3 grid, dim3 block, cudaStr
 static int ct_dispatch(CtKParams& k, int wf, bool backward, cudaStream_t st) {
   dim3 grid, block;
   int mats = 1;
-  bool stream = stream_shape(k, grid, block, mats);
+  bool stream = stream_shape(k, grid, block, mats, backward ? kPerWarpBwd : kPerWarpFwd);
   if (stream) {
     if (backward) stream = fits_i32(k.d_albedo, k.H, k.W) && fits_i32(k.d_normal, k.H, k.W) && fits_i32(k.d_roughness, k.H, k.W) && fits_i32(k.d_metspec, k.H, k.W);
     else stream = fits_i32(k.out, k.H, k.W);

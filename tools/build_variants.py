@@ -28,6 +28,12 @@ VARIANTS = {
     # geometry cache of the multi-light kernels (point lights, L > 1): off / backward register budget / light-loop unrolling
     "gc_off": ["-DPBR_GC_MAX_BYTES=0"],
     "gc_b3": v(bwd_cached_min_ctas=3),
+    "s_cta": v(stream_per_warp_fwd=0, stream_per_warp_bwd=0),
+    "s_pw": v(stream_per_warp_fwd=1, stream_per_warp_bwd=1),
+    "s_pw_late": v(stream_per_warp_fwd=1, stream_per_warp_bwd=1, stream_bwd_late_refill=1),
+    "s_pw_late3": v(stream_per_warp_fwd=1, stream_per_warp_bwd=1, stream_bwd_late_refill=1, stream_stages=3),
+    "s_pw3": v(stream_stages=3),
+    "s_pw4": v(stream_stages=4),
     "x_nopf": v(prefetch_next=0),
     "x_cold1": v(cold_unroll=1),
     "x_pl0": v(packed_loss=0),

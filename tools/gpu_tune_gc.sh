@@ -1,8 +1,5 @@
 #!/bin/bash
-# variants of the multi-light kernels on the C3 / C5 shapes (tools/tune.py)
 set +e
 mkdir -p gpurun_out
-echo "== L=16 accumulate B=16 1024^2"; TUNE_B=16 TUNE_L=16 timeout 600 python tools/tune.py 2>&1 | tail -12
-echo "== L=8 per-light fused loss B=32 1024^2"; TUNE_B=32 TUNE_L=8 TUNE_PER_LIGHT=1 timeout 600 python tools/tune.py 2>&1 | tail -12
-echo "== L=4 accumulate B=16"; TUNE_B=16 TUNE_L=4 timeout 600 python tools/tune.py 2>&1 | tail -12
-echo "== L=1 generic B=32 (PbrCtDesc.force_generic is not set by tune.py: streamed)"; TUNE_B=32 TUNE_L=1 timeout 600 python tools/tune.py 2>&1 | tail -12
+timeout 800 python -m pytest tests -m gpu -q -x --tb=short 2>&1 | grep -E "^E   |passed|failed" | cut -c1-260 | head -6
+echo "== L=1 B=64 1024^2"; TUNE_B=64 TUNE_L=1 timeout 600 python tools/tune.py 2>&1 | tail -6
