@@ -239,6 +239,10 @@ __device__ __forceinline__ void load_material(const CtKParams& p, const Where& w
 // The maps of the NEXT material of the walk are pulled into L2 while the current one is shaded (one request per 128-byte
 // line: a warp's row segment of a plane is 256 bytes), so the loads at the top of the next iteration hit L2 instead of
 // waiting for HBM.  No registers, no shared memory (the multi-light kernels have neither to spare).
+#ifndef PBR_FWD_REG_PREFETCH
+#define PBR_FWD_REG_PREFETCH 1
+#endif
+constexpr bool kFwdRegPrefetch = PBR_FWD_REG_PREFETCH != 0;
 #ifndef PBR_PREFETCH_NEXT
 #define PBR_PREFETCH_NEXT 1
 #endif
@@ -331,10 +335,25 @@ __global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kerne
 
   const int b0 = blockIdx.z * p.mats_per_cta;
   const int b1 = min(b0 + p.mats_per_cta, p.B);
+  // The forward has registers to spare (96 of the 128 its occupancy allows), so the maps of the next material of the walk
+  // are loaded into a second register set while the current one is shaded (the backward, at 235 registers, prefetches
+  // into L2 instead).
+  float nx_a[3][kCtTexels], nx_n[3][kCtTexels], nx_r[kCtTexels], nx_m[3][kCtTexels];
+  if (kFwdRegPrefetch) load_material<WF>(p, w, b0, nx_a, nx_n, nx_r, nx_m);
   for (int b = b0; b < b1; ++b) {
     float araw[3][kCtTexels], nraw[3][kCtTexels], rough[kCtTexels], mraw[3][kCtTexels];
-    load_material<WF>(p, w, b, araw, nraw, rough, mraw);
-    if (b + 1 < b1) prefetch_material<WF>(p, w, b + 1);
+    if (kFwdRegPrefetch) {
+#pragma unroll
+      for (int i = 0; i < kCtTexels; ++i) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { araw[c][i] = nx_a[c][i]; nraw[c][i] = nx_n[c][i]; mraw[c][i] = nx_m[c][i]; }
+        rough[i] = nx_r[i];
+      }
+      if (b + 1 < b1) load_material<WF>(p, w, b + 1, nx_a, nx_n, nx_r, nx_m);
+    } else {
+      load_material<WF>(p, w, b, araw, nraw, rough, mraw);
+      if (b + 1 < b1) prefetch_material<WF>(p, w, b + 1);
+    }
     float outv[3][kCtTexels];
 #pragma unroll
     for (int s = 0; s < kSlots; s += G) {

@@ -1,5 +1,7 @@
 #!/bin/bash
 set +e
 mkdir -p gpurun_out
-timeout 800 python -m pytest tests -m gpu -q -x --tb=short 2>&1 | grep -E "^E   |passed|failed" | cut -c1-260 | head -6
-echo "== L=1 B=64 1024^2"; TUNE_B=64 TUNE_L=1 timeout 600 python tools/tune.py 2>&1 | tail -6
+echo "== L=16 accumulate B=16 1024^2"; TUNE_B=16 TUNE_L=16 timeout 600 python tools/tune.py 2>&1 | tail -3
+echo "== L=8 per-light B=32 (fwd = per-light forward)"; TUNE_B=32 TUNE_L=8 TUNE_PER_LIGHT=1 timeout 600 python tools/tune.py 2>&1 | tail -3
+echo "== L=4 accumulate B=16"; TUNE_B=16 TUNE_L=4 timeout 600 python tools/tune.py 2>&1 | tail -3
+echo "== L=2 accumulate B=16"; TUNE_B=16 TUNE_L=2 timeout 600 python tools/tune.py 2>&1 | tail -3
