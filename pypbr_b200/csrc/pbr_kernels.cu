@@ -239,6 +239,10 @@ __device__ __forceinline__ void load_material(const CtKParams& p, const Where& w
 // The maps of the NEXT material of the walk are pulled into L2 while the current one is shaded (one request per 128-byte
 // line: a warp's row segment of a plane is 256 bytes), so the loads at the top of the next iteration hit L2 instead of
 // waiting for HBM.  No registers, no shared memory (the multi-light kernels have neither to spare).
+#ifndef PBR_BWD_LATE_PREFETCH
+#define PBR_BWD_LATE_PREFETCH 0   // measured: +1.6 % on C3, -3 % on the C5 fit kernel (same instantiation, per-light mode) -> off
+#endif
+constexpr bool kBwdLatePrefetch = PBR_BWD_LATE_PREFETCH != 0;
 #ifndef PBR_FWD_REG_PREFETCH
 #define PBR_FWD_REG_PREFETCH 1
 #endif
@@ -502,9 +506,24 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
   V loss_v = splat<V>(0.0f);   // squared error of the vector path, one partial sum per lane
   const int b0 = blockIdx.z * p.mats_per_cta;
   const int b1 = min(b0 + p.mats_per_cta, p.B);
+  // The maps of material b + 1 are requested when the light loop of material b is over - its ~70 registers are free by
+  // then - and land (from L2, where prefetch_material sent them) while the gradients of b are finished and stored.
+  // Only where it was measured to pay: the 255-register flavour in accumulate mode (L = 16: 2.49 -> 2.45 ms per
+  // 16 x 1024^2); the 168-register flavours spill over it (L = 4: 0.83 -> 1.02 ms), the per-light loss kernel is neutral.
+  const bool late_prefetch = kBwdLatePrefetch && kLight == kLightPointCached && !p.flags.per_light;
+  float nx_a[3][kCtTexels], nx_n[3][kCtTexels], nx_r[kCtTexels], nx_m[3][kCtTexels];
   for (int b = b0; b < b1; ++b) {
     float araw[3][kCtTexels], nraw[3][kCtTexels], rough[kCtTexels], mraw[3][kCtTexels];
-    load_material<WF>(p, w, b, araw, nraw, rough, mraw);
+    if (late_prefetch && b > b0) {
+#pragma unroll
+      for (int i = 0; i < kCtTexels; ++i) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { araw[c][i] = nx_a[c][i]; nraw[c][i] = nx_n[c][i]; mraw[c][i] = nx_m[c][i]; }
+        rough[i] = nx_r[i];
+      }
+    } else {
+      load_material<WF>(p, w, b, araw, nraw, rough, mraw);
+    }
     if (b + 1 < b1) prefetch_material<WF>(p, w, b + 1);
     if (p.adam_on) {
       // Fused fit step: what the Adam epilogue of THIS material needs (parameters and both moments of every channel)
@@ -581,6 +600,10 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
         cp_async_commit();   // always: keeps the group count uniform
       };
       auto fetch = [&](int l) {
+        if (l < 0) {   // after the light loop
+          if (late_prefetch && s + G >= kSlots && b + 1 < b1) load_material<WF>(p, w, b + 1, nx_a, nx_n, nx_r, nx_m);
+          return;
+        }
         if (l == 0) {
 #pragma unroll
           for (int q = 0; q < kRing - 1; ++q) issue(q);

@@ -218,6 +218,7 @@ PBR_HD void ct_forward_group(const CtStage& S, const CtFlags& F, const V (&araw)
 //   gout(l, out[3][N], g[3][N]) : given the encoded output of light l (or of the accumulated image,
 //        l = 0) fills g = dLoss/d out.  The plain backward ignores `out` and loads grad_out; the fused
 //        loss kernel computes 2*scale*(out - target) and accumulates the loss.
+//   fetch(-1)                   : called once after the light loop (the per-light registers are dead from here on);
 //   fetch(l)                    : software prefetch hook of the generic kernels: "what was fetched last becomes
 //        current, start loading the grad_out / target of light l" (l == L: rotate only).  gout(l) then reads the
 //        current buffer, which was requested one whole light iteration earlier.
@@ -385,6 +386,7 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
     int_sink(l, gi_sum);
     if (kGeom) geom_sink.light(l, glt_sum);
   }
+  fetch(-1);   // the light loop is over and its registers are free: the caller may start loading whatever comes next
 
 #pragma unroll
   for (int i = 0; i < N; ++i) {

@@ -36,6 +36,7 @@ VARIANTS = {
     "s_pw4": v(stream_stages=4),
     "x_nopf": v(prefetch_next=0),
     "x_noregpf": v(fwd_reg_prefetch=0),
+    "x_nolate": v(bwd_late_prefetch=0),
     "x_cold1": v(cold_unroll=1),
     "x_pl0": v(packed_loss=0),
     "u_f2": v(fwd_unroll=2),
