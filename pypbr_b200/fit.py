@@ -174,13 +174,13 @@ class FusedAdam:
     def step(self, grads: Dict[str, torch.Tensor], grad_scale: float = 1.0) -> None:
         """One Adam step with gradient `grads[name] * grad_scale` for every map (grads are not modified)."""
         lib = _cabi.load()
-        self.step_count += 1
+        t_step = self.step_count + 1   # committed only once the launch has been accepted
         b1, b2 = self.betas
         d = _cabi.PbrAdamDesc()
         d.B, d.H, d.W, d.n_maps = self.B, self.H, self.W, len(self.params)
-        d.step_size = self.lr / (1.0 - b1 ** self.step_count)
+        d.step_size = self.lr / (1.0 - b1 ** t_step)
         d.one_minus_beta1, d.beta2, d.one_minus_beta2 = 1.0 - b1, b2, 1.0 - b2
-        d.bias2_sqrt = (1.0 - b2 ** self.step_count) ** 0.5
+        d.bias2_sqrt = (1.0 - b2 ** t_step) ** 0.5
         d.eps, d.grad_scale = self.eps, float(grad_scale)
         device = None
         for i, (name, t) in enumerate(self.params.items()):
@@ -196,6 +196,7 @@ class FusedAdam:
             device = t.device
         with torch.cuda.device(device):
             _cabi.check(lib.pbr_adam_step(_cabi.byref(d), _cabi.stream_ptr(device)), "pbr_adam_step")
+        self.step_count = t_step
 
 
 def fused_fit_step(
@@ -261,7 +262,7 @@ def fused_fit_step(
     ls.target, ls.target_sl = _out_plane(target, cfg.per_light, cfg.batched)
     ls.loss_scale = float(loss_scale)
     ls.loss_sum = red.data_ptr()
-    optimizer.step_count += 1
+    t = optimizer.step_count + 1   # committed only once the launch has been accepted
     b1, b2 = optimizer.betas
     a = _cabi.PbrCtAdam()
     for key, name in (("albedo", "albedo"), ("normal", "normal"), ("roughness", "roughness"), ("metspec", met_name)):
@@ -269,9 +270,9 @@ def fused_fit_step(
             m, v = optimizer.state[name]
             setattr(a, "m_" + key, _cabi.plane(m))
             setattr(a, "v_" + key, _cabi.plane(v))
-    a.step_size = optimizer.lr / (1.0 - b1 ** optimizer.step_count)
+    a.step_size = optimizer.lr / (1.0 - b1 ** t)
     a.one_minus_beta1, a.beta2, a.one_minus_beta2 = 1.0 - b1, b2, 1.0 - b2
-    a.bias2_sqrt = (1.0 - b2 ** optimizer.step_count) ** 0.5
+    a.bias2_sqrt = (1.0 - b2 ** t) ** 0.5
     a.eps = optimizer.eps
     a.project = 1 if kinds == {True} else 0
     d_int = ctypes.c_void_p(red[1:].data_ptr()) if want_intensity_grad else None
@@ -280,6 +281,7 @@ def fused_fit_step(
             lib.pbr_ct_fit_step(_cabi.byref(d), _cabi.byref(ls), _cabi.byref(a), d_int, _cabi.stream_ptr(device)),
             "pbr_ct_fit_step",
         )
+    optimizer.step_count = t
     return red
 
 
