@@ -17,6 +17,16 @@
 #include "../../include/pbrcuda.h"
 #include "pbr_shade.cuh"
 
+// Build-time split (__graft_entry__.build_cuda): the Cook-Torrance kernels are instantiated per workflow (WF = 0 metallic,
+// 1 specular, 2 metallic with a 3-channel map), a third of the compile time each.  -DPBR_PART=k compiles only the
+// instantiations of workflow k and their launcher (pbr::launch_wf<k>); part 0 also holds the streaming kernels, the
+// dispatch and the C ABI.  Without PBR_PART everything lands in one translation unit (same code, three times the wait).
+#ifndef PBR_PART
+#define PBR_PART (-1)
+#endif
+#define PBR_MAIN_PART (PBR_PART <= 0)
+#define PBR_HAS_WF(k) (PBR_PART < 0 || PBR_PART == (k))
+
 namespace pbr {
 
 #ifndef PBR_THREADS
@@ -804,6 +814,8 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
 
 #include "pbr_ct_stream.cuh"
 
+#if PBR_MAIN_PART
+
 namespace pbr {
 
 // ------------------------------------------------------------------------------------------------
@@ -1003,6 +1015,8 @@ __global__ void __launch_bounds__(kThreads) normal_ingest_kernel(const __grid_co
 }  // namespace pbr
 
 #include "pbr_aux_kernels.cuh"
+#endif   // PBR_MAIN_PART
+
 
 namespace pbr {
 
@@ -1245,6 +1259,31 @@ static void launch_bwd_stream(const CtKParams& k, dim3 grid, dim3 block, cudaStr
   }
 }
 
+// every Cook-Torrance kernel of one workflow behind one plain function (see PBR_PART at the top of this file)
+template <int WF>
+static void launch_wf(CtKParams& k, dim3 grid, dim3 block, bool stream, bool backward, cudaStream_t st) {
+  if (stream) {
+    if (backward) launch_bwd_stream<WF>(k, grid, block, st);
+    else launch_fwd_stream<WF>(k, grid, block, st);
+  } else {
+    if (backward) launch_bwd<WF>(k, grid, block, st);
+    else launch_fwd<WF>(k, grid, block, st);
+  }
+}
+void launch_wf0(CtKParams& k, dim3 grid, dim3 block, bool stream, bool backward, cudaStream_t st);
+void launch_wf1(CtKParams& k, dim3 grid, dim3 block, bool stream, bool backward, cudaStream_t st);
+void launch_wf2(CtKParams& k, dim3 grid, dim3 block, bool stream, bool backward, cudaStream_t st);
+#if PBR_HAS_WF(0)
+void launch_wf0(CtKParams& k, dim3 grid, dim3 block, bool stream, bool backward, cudaStream_t st) { launch_wf<0>(k, grid, block, stream, backward, st); }
+#endif
+#if PBR_HAS_WF(1)
+void launch_wf1(CtKParams& k, dim3 grid, dim3 block, bool stream, bool backward, cudaStream_t st) { launch_wf<1>(k, grid, block, stream, backward, st); }
+#endif
+#if PBR_HAS_WF(2)
+void launch_wf2(CtKParams& k, dim3 grid, dim3 block, bool stream, bool backward, cudaStream_t st) { launch_wf<2>(k, grid, block, stream, backward, st); }
+#endif
+
+#if PBR_MAIN_PART
 // shared tail of the three Cook-Torrance entry points
 static int ct_dispatch(CtKParams& k, int wf, bool backward, cudaStream_t st) {
   dim3 grid, block;
@@ -1254,42 +1293,20 @@ static int ct_dispatch(CtKParams& k, int wf, bool backward, cudaStream_t st) {
     if (backward) stream = fits_i32(k.d_albedo, k.H, k.W) && fits_i32(k.d_normal, k.H, k.W) && fits_i32(k.d_roughness, k.H, k.W) && fits_i32(k.d_metspec, k.H, k.W);
     else stream = fits_i32(k.out, k.H, k.W);
   }
-  if (stream) {
-    k.mats_per_cta = mats;
-    if (backward) {
-      switch (wf) {
-        case 0: launch_bwd_stream<0>(k, grid, block, st); break;
-        case 1: launch_bwd_stream<1>(k, grid, block, st); break;
-        default: launch_bwd_stream<2>(k, grid, block, st); break;
-      }
-    } else {
-      switch (wf) {
-        case 0: launch_fwd_stream<0>(k, grid, block, st); break;
-        case 1: launch_fwd_stream<1>(k, grid, block, st); break;
-        default: launch_fwd_stream<2>(k, grid, block, st); break;
-      }
-    }
-    return launch_result();
-  }
-  ct_launch_shape(k, grid, block);
-  if (backward) {
-    switch (wf) {
-      case 0: launch_bwd<0>(k, grid, block, st); break;
-      case 1: launch_bwd<1>(k, grid, block, st); break;
-      default: launch_bwd<2>(k, grid, block, st); break;
-    }
-  } else {
-    switch (wf) {
-      case 0: launch_fwd<0>(k, grid, block, st); break;
-      case 1: launch_fwd<1>(k, grid, block, st); break;
-      default: launch_fwd<2>(k, grid, block, st); break;
-    }
+  if (stream) k.mats_per_cta = mats;
+  else ct_launch_shape(k, grid, block);
+  switch (wf) {
+    case 0: launch_wf0(k, grid, block, stream, backward, st); break;
+    case 1: launch_wf1(k, grid, block, stream, backward, st); break;
+    default: launch_wf2(k, grid, block, stream, backward, st); break;
   }
   return launch_result();
 }
+#endif   // PBR_MAIN_PART
 
 }  // namespace pbr
 
+#if PBR_MAIN_PART
 using namespace pbr;
 
 extern "C" {
@@ -1578,3 +1595,4 @@ int pbr_normal_op(const PbrNormalOpDesc* d, pbr_stream_t stream) {
 }
 
 }  // extern "C"
+#endif   // PBR_MAIN_PART
