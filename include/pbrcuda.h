@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PBR_ABI_VERSION 4
+#define PBR_ABI_VERSION 5
 #define PBR_MAX_LIGHTS 64      /* lights per launch (parameters are staged in shared memory) */
 #define PBR_MAX_BLEND_MAPS 12  /* maps blended by one pbr_blend launch */
 #define PBR_MAX_INDEX_MAPS 12  /* maps moved by one pbr_index_transform launch */
@@ -126,10 +126,27 @@ typedef struct PbrConvDesc {
   int32_t B, H, W;
   int32_t albedo_is_srgb;
   PbrPlane albedo;          /* in, 3 ch */
-  PbrPlane metspec;         /* in: metallic 1 ch (m2s) / raw specular 3 ch (s2m) */
+  PbrPlane metspec;         /* in: metallic 1 ch or 3 ch (m2s, see metallic_channels) / raw specular 3 ch (s2m) */
   PbrPlane out0;            /* out 3 ch: diffuse (m2s) / basecolor (s2m) */
   PbrPlane out1;            /* out 3 ch: specular (m2s) / metallic, 3 channels (s2m) */
+  int32_t metallic_channels;/* m2s: 1 (usual; 0 means 1) or 3 - the per-channel metallic s2m produces (diffuse.py:150-156);
+                               the reference broadcasts either against the 3-channel albedo (metallic.py:103-106) */
 } PbrConvDesc;
+
+/*
+ * Adjoints of the two conversions (the reference's are plain differentiable torch ops, metallic.py:103-109 and
+ * diffuse.py:129-147, so a fit that goes through a conversion back-propagates through it): recompute the forward
+ * per texel, follow autograd's conventions (inclusive clamp gates, torch.where routes, the sRGB decode slope).
+ *   m2s: d_albedo = (g0 (1-m) + g1 m) decode'(albedo);  d_metallic = sum_c [-g0_c a_c + g1_c (a_c - 0.04)]
+ *        (per channel for a 3-channel metallic);  s2m: through clamp / where / the two divisions (see the kernel).
+ * `desc` is the forward's descriptor (out0 / out1 are ignored).  g_out*.ptr == NULL means a zero gradient; d_*.ptr ==
+ * NULL means not required.
+ */
+typedef struct PbrConvGrads {
+  PbrPlane g_out0, g_out1;  /* 3 ch each: gradients w.r.t. the forward's two outputs */
+  PbrPlane d_albedo;        /* 3 ch */
+  PbrPlane d_metspec;       /* m2s: 1 or 3 ch (metallic_channels); s2m: 3 ch (raw specular) */
+} PbrConvGrads;
 
 /*
  * Blending.  Replaces blend_with_mask / _blend_normals / blend_on_height / blend_on_properties /
@@ -159,6 +176,25 @@ typedef struct PbrBlendDesc {
   PbrBlendMap maps[PBR_MAX_BLEND_MAPS];
 } PbrBlendDesc;
 
+/*
+ * Adjoint of pbr_blend (functional.py:104-108 and :134-143 are plain differentiable torch ops in the reference).
+ * `desc` is the forward's descriptor (maps[i].out, mask_out and normal_min are ignored); `mask` is the mask the forward
+ * used: the given one, or the mask_out it wrote.  Per map i: d_a = mask g, d_b = (1-mask) g, through the three
+ * normalisations for a normal map; d_mask = g_mask_out + sum over maps and channels of g (a - b);
+ * SIGMOID: d_prop1 = d_mask mask (1 - mask) / (blend_width + 1e-6), d_prop2 = -d_prop1 (GRADIENT modes have no mask input).
+ * NULL pointers: g_out -> zero gradient, d_* -> not required.
+ */
+typedef struct PbrBlendGradMap {
+  PbrPlane g_out, d_a, d_b; /* same channel count as desc->maps[i] */
+} PbrBlendGradMap;
+typedef struct PbrBlendGrads {
+  PbrPlane mask;            /* 1 ch, required */
+  PbrPlane g_mask_out;      /* 1 ch: gradient flowing into the returned mask; may be NULL */
+  PbrPlane d_mask;          /* GIVEN: 1 ch; may be NULL */
+  PbrPlane d_prop1, d_prop2;/* SIGMOID: 1 ch each; may be NULL */
+  PbrBlendGradMap maps[PBR_MAX_BLEND_MAPS];
+} PbrBlendGrads;
+
 /* sRGB <-> linear on an arbitrary C-channel map (pypbr/utils/functions.py:31-66). to_linear: 1 = decode, 0 = encode. */
 typedef struct PbrColorDesc {
   int32_t B, C, H, W;
@@ -175,8 +211,17 @@ typedef struct PbrColorDesc {
 typedef struct PbrNormalDesc {
   int32_t B, H, W;
   int32_t channels;         /* of `in`: 2 or 3; `out` always has 3 */
-  PbrPlane in, out;
+  PbrPlane in, out;         /* channels == 3: in == out is allowed (each thread reads its texels before it writes them) */
+  const float* cond_min;    /* pbr_normal_ingest only, optional DEVICE scalar: the launch does nothing when *cond_min < 0.
+                               It carries base.py:212's decision `normal_map.min() < 0 -> keep as is` for a probe result that
+                               is still on the device (pbr_blend's normal_min), so the host never reads it back */
 } PbrNormalDesc;
+
+/* Adjoint of pbr_normal_ingest (base.py:215-217 / :235-242 are differentiable torch ops): `desc->in` is the forward's
+   input (desc->out is ignored), g_out the gradient w.r.t. its 3-channel output, d_in receives `channels` channels. */
+typedef struct PbrNormalGrads {
+  PbrPlane g_out, d_in;
+} PbrNormalGrads;
 
 /*
  * Image ingestion - the step before the shading path.  Replaces
@@ -216,6 +261,9 @@ typedef struct PbrIndexDesc {
   int32_t origin_y, step_y, origin_x, step_x;
   int32_t wrap;
   int32_t n_maps;
+  /* Adjoint of a tile (tensor.repeat): out[y, x] = sum over i < reduce_y, j < reduce_x of the formula above evaluated at
+     (y + i*H_out, x + j*W_out).  0 or 1 = plain gather.  The adjoints of flip and roll are gathers themselves. */
+  int32_t reduce_y, reduce_x;
   PbrIndexMap maps[PBR_MAX_INDEX_MAPS];
 } PbrIndexDesc;
 
@@ -298,10 +346,14 @@ int pbr_ct_fit_step(const PbrCtDesc* desc, const PbrCtLoss* loss, const PbrCtAda
 
 int pbr_convert_m2s(const PbrConvDesc* desc, pbr_stream_t stream);
 int pbr_convert_s2m(const PbrConvDesc* desc, pbr_stream_t stream);
+int pbr_convert_m2s_backward(const PbrConvDesc* desc, const PbrConvGrads* grads, pbr_stream_t stream);
+int pbr_convert_s2m_backward(const PbrConvDesc* desc, const PbrConvGrads* grads, pbr_stream_t stream);
 int pbr_blend(const PbrBlendDesc* desc, pbr_stream_t stream);
+int pbr_blend_backward(const PbrBlendDesc* desc, const PbrBlendGrads* grads, pbr_stream_t stream);
 int pbr_color_convert(const PbrColorDesc* desc, pbr_stream_t stream);
 int pbr_normal_min(const PbrNormalDesc* desc, float* result, pbr_stream_t stream);
 int pbr_normal_ingest(const PbrNormalDesc* desc, pbr_stream_t stream);
+int pbr_normal_ingest_backward(const PbrNormalDesc* desc, const PbrNormalGrads* grads, pbr_stream_t stream);
 int pbr_ingest_image(const PbrIngestDesc* desc, pbr_stream_t stream);
 int pbr_index_transform(const PbrIndexDesc* desc, pbr_stream_t stream);
 int pbr_adam_step(const PbrAdamDesc* desc, pbr_stream_t stream);
@@ -309,7 +361,8 @@ int pbr_normal_op(const PbrNormalOpDesc* desc, pbr_stream_t stream);
 
 /* sizeof() of the descriptor structs as THIS library was compiled (binding self-check):
    which = 0 PbrPlane, 1 PbrCtDesc, 2 PbrCtGrads, 3 PbrCtLoss, 4 PbrConvDesc, 5 PbrBlendMap, 6 PbrBlendDesc,
-   7 PbrColorDesc, 8 PbrNormalDesc, 9 PbrIngestDesc, 10 PbrIndexMap, 11 PbrIndexDesc, 12 PbrAdamMap, 13 PbrAdamDesc, 14 PbrCtAdam, 15 PbrNormalOpDesc;
+   7 PbrColorDesc, 8 PbrNormalDesc, 9 PbrIngestDesc, 10 PbrIndexMap, 11 PbrIndexDesc, 12 PbrAdamMap, 13 PbrAdamDesc, 14 PbrCtAdam, 15 PbrNormalOpDesc,
+   16 PbrConvGrads, 17 PbrBlendGradMap, 18 PbrBlendGrads, 19 PbrNormalGrads;
    anything else returns 0. */
 uint64_t pbr_sizeof(int which);
 

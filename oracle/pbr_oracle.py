@@ -124,8 +124,9 @@ def shade_linear(
         lpos = light.view(3, 1, 1)
         s = light_size or 1.0
         # linspace stays fp32 in the reference even when the maps are fp64 (it promotes afterwards)
-        x = torch.linspace(-s / 2, s / 2, W)
-        y = torch.linspace(-s / 2, s / 2, H)
+        # (device=: the reference builds the grid on `device`, cooktorrance.py:132-133; the CPU default is unchanged)
+        x = torch.linspace(-s / 2, s / 2, W, device=base.device)
+        y = torch.linspace(-s / 2, s / 2, H, device=base.device)
         yv, xv = torch.meshgrid(y, x, indexing="ij")
         pos = torch.stack([xv, -yv, torch.zeros_like(xv)], dim=0)
         lmap = lpos - pos
@@ -136,7 +137,7 @@ def shade_linear(
         raise ValueError("Invalid light_type")
 
     if nmap is None:  # :143-151
-        nmap = torch.tensor([0.0, 0.0, 1.0], dtype=dt).view(3, 1, 1).expand(3, H, W)
+        nmap = torch.tensor([0.0, 0.0, 1.0], dtype=dt, device=base.device).view(3, 1, 1).expand(3, H, W)
     n = F.normalize(nmap, dim=0)  # :153
     h = F.normalize(vmap + lmap, dim=0)  # :154
     cos_t = torch.clamp((h * vmap).sum(dim=0, keepdim=True), 0.0, 1.0)  # :155-157

@@ -16,7 +16,7 @@ from typing import Optional, Sequence
 
 import torch
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 PBR_MAX_LIGHTS = 64
 PBR_MAX_BLEND_MAPS = 12
 PBR_MAX_INDEX_MAPS = 12
@@ -67,7 +67,12 @@ class PbrConvDesc(Structure):
     _fields_ = [
         ("B", c_int32), ("H", c_int32), ("W", c_int32), ("albedo_is_srgb", c_int32),
         ("albedo", PbrPlane), ("metspec", PbrPlane), ("out0", PbrPlane), ("out1", PbrPlane),
+        ("metallic_channels", c_int32),
     ]
+
+
+class PbrConvGrads(Structure):
+    _fields_ = [("g_out0", PbrPlane), ("g_out1", PbrPlane), ("d_albedo", PbrPlane), ("d_metspec", PbrPlane)]
 
 
 class PbrBlendMap(Structure):
@@ -84,6 +89,17 @@ class PbrBlendDesc(Structure):
     ]
 
 
+class PbrBlendGradMap(Structure):
+    _fields_ = [("g_out", PbrPlane), ("d_a", PbrPlane), ("d_b", PbrPlane)]
+
+
+class PbrBlendGrads(Structure):
+    _fields_ = [
+        ("mask", PbrPlane), ("g_mask_out", PbrPlane), ("d_mask", PbrPlane), ("d_prop1", PbrPlane), ("d_prop2", PbrPlane),
+        ("maps", PbrBlendGradMap * PBR_MAX_BLEND_MAPS),
+    ]
+
+
 class PbrColorDesc(Structure):
     _fields_ = [
         ("B", c_int32), ("C", c_int32), ("H", c_int32), ("W", c_int32), ("to_linear", c_int32),
@@ -92,7 +108,12 @@ class PbrColorDesc(Structure):
 
 
 class PbrNormalDesc(Structure):
-    _fields_ = [("B", c_int32), ("H", c_int32), ("W", c_int32), ("channels", c_int32), ("in_", PbrPlane), ("out", PbrPlane)]
+    _fields_ = [("B", c_int32), ("H", c_int32), ("W", c_int32), ("channels", c_int32), ("in_", PbrPlane), ("out", PbrPlane),
+                ("cond_min", c_void_p)]
+
+
+class PbrNormalGrads(Structure):
+    _fields_ = [("g_out", PbrPlane), ("d_in", PbrPlane)]
 
 
 class PbrIngestDesc(Structure):
@@ -112,7 +133,7 @@ class PbrIndexDesc(Structure):
     _fields_ = [
         ("B", c_int32), ("H_in", c_int32), ("W_in", c_int32), ("H_out", c_int32), ("W_out", c_int32),
         ("origin_y", c_int32), ("step_y", c_int32), ("origin_x", c_int32), ("step_x", c_int32),
-        ("wrap", c_int32), ("n_maps", c_int32),
+        ("wrap", c_int32), ("n_maps", c_int32), ("reduce_y", c_int32), ("reduce_x", c_int32),
         ("maps", PbrIndexMap * PBR_MAX_INDEX_MAPS),
     ]
 
@@ -154,7 +175,8 @@ NORMAL_OP_ROTATE, NORMAL_OP_FROM_HEIGHT, NORMAL_OP_DIVERGENCE = 0, 1, 2
 
 # order = the `which` argument of pbr_sizeof()
 STRUCTS = (PbrPlane, PbrCtDesc, PbrCtGrads, PbrCtLoss, PbrConvDesc, PbrBlendMap, PbrBlendDesc, PbrColorDesc, PbrNormalDesc,
-           PbrIngestDesc, PbrIndexMap, PbrIndexDesc, PbrAdamMap, PbrAdamDesc, PbrCtAdam, PbrNormalOpDesc)
+           PbrIngestDesc, PbrIndexMap, PbrIndexDesc, PbrAdamMap, PbrAdamDesc, PbrCtAdam, PbrNormalOpDesc,
+           PbrConvGrads, PbrBlendGradMap, PbrBlendGrads, PbrNormalGrads)
 
 _lib = None
 
@@ -163,6 +185,7 @@ EXPORTS = (
     "pbr_abi_version", "pbr_strerror", "pbr_ct_forward", "pbr_ct_backward", "pbr_ct_loss_fwd_bwd", "pbr_ct_fit_step",
     "pbr_convert_m2s", "pbr_convert_s2m", "pbr_blend", "pbr_color_convert", "pbr_normal_min",
     "pbr_normal_ingest", "pbr_ingest_image", "pbr_index_transform", "pbr_adam_step", "pbr_normal_op", "pbr_launch_count", "pbr_sizeof",
+    "pbr_convert_m2s_backward", "pbr_convert_s2m_backward", "pbr_blend_backward", "pbr_normal_ingest_backward",
 )
 
 
@@ -195,6 +218,10 @@ def load():
     lib.pbr_convert_m2s.argtypes = [POINTER(PbrConvDesc), c_void_p]
     lib.pbr_convert_s2m.argtypes = [POINTER(PbrConvDesc), c_void_p]
     lib.pbr_blend.argtypes = [POINTER(PbrBlendDesc), c_void_p]
+    lib.pbr_convert_m2s_backward.argtypes = [POINTER(PbrConvDesc), POINTER(PbrConvGrads), c_void_p]
+    lib.pbr_convert_s2m_backward.argtypes = [POINTER(PbrConvDesc), POINTER(PbrConvGrads), c_void_p]
+    lib.pbr_blend_backward.argtypes = [POINTER(PbrBlendDesc), POINTER(PbrBlendGrads), c_void_p]
+    lib.pbr_normal_ingest_backward.argtypes = [POINTER(PbrNormalDesc), POINTER(PbrNormalGrads), c_void_p]
     lib.pbr_color_convert.argtypes = [POINTER(PbrColorDesc), c_void_p]
     lib.pbr_normal_min.argtypes = [POINTER(PbrNormalDesc), c_void_p, c_void_p]
     lib.pbr_normal_ingest.argtypes = [POINTER(PbrNormalDesc), c_void_p]
@@ -252,6 +279,14 @@ def plane(t: Optional[torch.Tensor]) -> PbrPlane:
     if t.dim() == 4:
         return PbrPlane(t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
     raise ValueError(f"maps must be (C,H,W) or (B,C,H,W), got shape {tuple(t.shape)}")
+
+
+def touch(*tensors) -> None:
+    """A kernel has written these tensors IN PLACE through their raw pointers: bump torch's version counter, so that
+    autograd notices a modified saved tensor and the memoised normal-map probe (materials/base.py) is invalidated."""
+    for t in tensors:
+        if t is not None:
+            torch.autograd.graph.increment_version(t)
 
 
 def stream_ptr(device: torch.device) -> c_void_p:

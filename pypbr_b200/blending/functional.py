@@ -16,7 +16,7 @@ import torch
 
 from .. import _cabi
 from ..materials import MaterialBase
-from ..materials.base import _normal_ingest_cuda
+from ..materials.base import _normal_ingest_cuda, normal_ingest
 
 
 def blend_materials(material1: MaterialBase, material2: MaterialBase, method: str = "mask", **kwargs) -> MaterialBase:
@@ -53,10 +53,139 @@ def _common_device(material1: MaterialBase, material2: MaterialBase) -> torch.de
     raise ValueError("Materials must have at least one map to blend.")
 
 
+class _BlendMeta:
+    """Everything about one blend that is not a tensor."""
+
+    __slots__ = ("B", "H", "W", "batched", "mode", "blend_width", "shift", "apply_shift", "device", "jobs")
+
+
+def _fill_blend_desc(meta: _BlendMeta) -> "_cabi.PbrBlendDesc":
+    d = _cabi.PbrBlendDesc()
+    d.B, d.H, d.W = meta.B, meta.H, meta.W
+    d.mask_mode = meta.mode
+    d.blend_width, d.shift, d.apply_shift = float(meta.blend_width), float(meta.shift), int(meta.apply_shift)
+    return d
+
+
+def _blend_launch(meta: _BlendMeta, lead, maps):
+    """pbr_blend over every (a, b) pair of `maps` (chunks of PBR_MAX_BLEND_MAPS).  lead: (mask,) | (prop1, prop2) | ().
+    Returns (mask written by the kernel or None, outputs, device scalar min(blended normal))."""
+    lib = _cabi.load()
+    device = meta.device
+    d = _fill_blend_desc(meta)
+    mask_out = None
+    if meta.mode == _cabi.MASK_GIVEN:
+        d.mask = _cabi.plane(lead[0])
+    else:
+        if meta.mode == _cabi.MASK_SIGMOID:
+            d.prop1, d.prop2 = _cabi.plane(lead[0]), _cabi.plane(lead[1])
+        mask_out = torch.empty((meta.B, 1, meta.H, meta.W) if meta.batched else (1, meta.H, meta.W), dtype=torch.float32, device=device)
+        d.mask_out = _cabi.plane(mask_out)
+    normal_min = torch.full((1,), float("inf"), dtype=torch.float32, device=device)
+    outs = [torch.empty(maps[2 * i].shape, dtype=torch.float32, device=device) for i in range(len(meta.jobs))]
+    with torch.cuda.device(device):
+        first = True
+        chunk = _cabi.PBR_MAX_BLEND_MAPS
+        for start in range(0, max(len(meta.jobs), 1), chunk):
+            part = range(start, min(start + chunk, len(meta.jobs)))
+            d.n_maps = len(part)
+            for i, j in enumerate(part):
+                _name, ch, is_normal = meta.jobs[j]
+                d.maps[i] = _cabi.PbrBlendMap(_cabi.plane(maps[2 * j]), _cabi.plane(maps[2 * j + 1]), _cabi.plane(outs[j]), ch, int(is_normal))
+            d.normal_min = normal_min.data_ptr() if any(meta.jobs[j][2] for j in part) else None
+            if not first:
+                d.mask_out = _cabi.PbrPlane(None, 0, 0, 0)  # already written by the first launch
+            _cabi.check(lib.pbr_blend(_cabi.byref(d), _cabi.stream_ptr(device)), "pbr_blend")
+            first = False
+    return mask_out, outs, normal_min
+
+
+class _BlendFn(torch.autograd.Function):
+    """
+    pbr_blend with its adjoint (pbr_blend_backward).  The reference's blend is a chain of differentiable torch ops
+    (functional.py:104-108, :134-143, :187-194), so a fit that goes through a blend needs d_a = mask g, d_b = (1-mask) g,
+    the three normalisations of a normal map, and the mask's own gradient (to the given mask, or through the sigmoid to
+    the two height / property maps).
+    Inputs: meta, then lead tensors ((mask,) | (prop1, prop2) | ()), then a0, b0, a1, b1, ...
+    Outputs: (the mask the kernel wrote | a dummy for GIVEN, min(blended normal), out0, out1, ...).
+    """
+
+    @staticmethod
+    def forward(ctx, meta: _BlendMeta, n_lead: int, *tensors):
+        lead = [t.detach() for t in tensors[:n_lead]]
+        maps = [t.detach() for t in tensors[n_lead:]]
+        mask_out, outs, normal_min = _blend_launch(meta, lead, maps)
+        ctx.meta, ctx.n_lead = meta, n_lead
+        used = lead[0] if meta.mode == _cabi.MASK_GIVEN else mask_out
+        ctx.save_for_backward(used, *lead, *maps)
+        if mask_out is None:
+            mask_out = torch.empty(0, device=meta.device)
+        ctx.mark_non_differentiable(normal_min)
+        if meta.mode == _cabi.MASK_GIVEN:
+            ctx.mark_non_differentiable(mask_out)
+        return (mask_out, normal_min, *outs)
+
+    @staticmethod
+    def backward(ctx, g_mask_out, _g_min, *g_outs):
+        meta, n_lead = ctx.meta, ctx.n_lead
+        used, *rest = ctx.saved_tensors
+        lead, maps = rest[:n_lead], rest[n_lead:]
+        lib = _cabi.load()
+        device = meta.device
+        need = ctx.needs_input_grad[2:]
+        need_lead, need_maps = need[:n_lead], need[n_lead:]
+        d_lead = [torch.empty(t.shape, dtype=torch.float32, device=device) if n else None for t, n in zip(lead, need_lead)]
+        d_maps = []
+        for j in range(len(meta.jobs)):
+            g = g_outs[j]
+            for side in (0, 1):
+                if not need_maps[2 * j + side]:
+                    d_maps.append(None)
+                elif g is None:   # zero gradient into this map's output: the kernel skips it
+                    d_maps.append(torch.zeros(maps[2 * j + side].shape, dtype=torch.float32, device=device))
+                else:
+                    d_maps.append(torch.empty(maps[2 * j + side].shape, dtype=torch.float32, device=device))
+        given = meta.mode == _cabi.MASK_GIVEN
+        g_mask = None if (given or g_mask_out is None) else _cabi.rowmajor(g_mask_out)
+        chunk = _cabi.PBR_MAX_BLEND_MAPS
+        starts = list(range(0, max(len(meta.jobs), 1), chunk))
+        carry = g_mask
+        keep = []
+        with torch.cuda.device(device):
+            for ci, start in enumerate(starts):
+                last = ci == len(starts) - 1
+                part = range(start, min(start + chunk, len(meta.jobs)))
+                d = _fill_blend_desc(meta)
+                gr = _cabi.PbrBlendGrads()
+                gr.mask = _cabi.plane(used)
+                gr.g_mask_out = _cabi.plane(carry)
+                if not last:
+                    # more maps than one launch takes: intermediate launches only accumulate the raw mask gradient
+                    d.mask_mode = _cabi.MASK_GIVEN
+                    carry = torch.empty(used.shape, dtype=torch.float32, device=device)
+                    keep.append(carry)
+                    gr.d_mask = _cabi.plane(carry)
+                elif given:
+                    gr.d_mask = _cabi.plane(d_lead[0]) if d_lead else _cabi.plane(None)
+                elif meta.mode == _cabi.MASK_SIGMOID:
+                    gr.d_prop1, gr.d_prop2 = _cabi.plane(d_lead[0]), _cabi.plane(d_lead[1])
+                d.n_maps = len(part)
+                for i, j in enumerate(part):
+                    _name, ch, is_normal = meta.jobs[j]
+                    d.maps[i] = _cabi.PbrBlendMap(_cabi.plane(maps[2 * j]), _cabi.plane(maps[2 * j + 1]), _cabi.plane(None), ch, int(is_normal))
+                    g = g_outs[j]
+                    if g is not None:
+                        g = _cabi.rowmajor(g)
+                        keep.append(g)
+                    gr.maps[i] = _cabi.PbrBlendGradMap(_cabi.plane(g), _cabi.plane(d_maps[2 * j] if g is not None else None),
+                                                       _cabi.plane(d_maps[2 * j + 1] if g is not None else None))
+                _cabi.check(lib.pbr_blend_backward(_cabi.byref(d), _cabi.byref(gr), _cabi.stream_ptr(device)), "pbr_blend_backward")
+        return (None, None, *d_lead, *d_maps)
+
+
 def _run_blend(material1: MaterialBase, material2: MaterialBase, mode: int, mask=None, prop1=None, prop2=None,
                blend_width: float = 0.0, shift: float = 0.0, apply_shift: bool = False, size=None):
     """Shared tail of every blend_* function: pypbr/blending/functional.py:76-116."""
-    lib = _cabi.load()
     device = _common_device(material1, material2)
     blended = material1.__class__()
 
@@ -83,8 +212,8 @@ def _run_blend(material1: MaterialBase, material2: MaterialBase, mode: int, mask
         B = max([t.shape[0] for _, a, b in pairs for t in (a, b) if t.dim() == 4] + ([mask.shape[0]] if (mask is not None and mask.dim() == 4) else []))
 
     def conform(t: torch.Tensor, channels: Optional[int], what: str) -> torch.Tensor:
+        # view ops only (unsqueeze / expand / contiguous): the autograd graph of a map that requires grad stays attached
         _cabi.require_cuda(t, what)
-        t = t.detach()
         if batched and t.dim() == 3:
             t = t.unsqueeze(0)
         if tuple(t.shape[-2:]) != (H, W):
@@ -99,53 +228,34 @@ def _run_blend(material1: MaterialBase, material2: MaterialBase, mode: int, mask
             t = t.expand(B, *t.shape[1:])
         return _cabi.rowmajor(t)
 
-    keep = []
-    mask_out = None
-    d = _cabi.PbrBlendDesc()
-    d.B, d.H, d.W = B, H, W
-    d.mask_mode = mode
-    d.blend_width, d.shift, d.apply_shift = float(blend_width), float(shift), int(apply_shift)
+    meta = _BlendMeta()
+    meta.B, meta.H, meta.W, meta.batched, meta.mode, meta.device = B, H, W, batched, mode, device
+    meta.blend_width, meta.shift, meta.apply_shift = blend_width, shift, apply_shift
+    lead = []
     if mode == _cabi.MASK_GIVEN:
-        mk = conform(mask.to(device), 1, "mask")
-        keep.append(mk)
-        d.mask = _cabi.plane(mk)
-    else:
-        if mode == _cabi.MASK_SIGMOID:
-            p1, p2 = conform(prop1, 1, "property map 1"), conform(prop2, 1, "property map 2")
-            keep.extend((p1, p2))
-            d.prop1, d.prop2 = _cabi.plane(p1), _cabi.plane(p2)
-        mask_out = torch.empty((B, 1, H, W) if batched else (1, H, W), dtype=torch.float32, device=device)
-        d.mask_out = _cabi.plane(mask_out)
-
-    normal_min = torch.full((1,), float("inf"), dtype=torch.float32, device=device)
-    outs = {}
-    jobs = []
+        lead = [conform(mask.to(device), 1, "mask")]
+    elif mode == _cabi.MASK_SIGMOID:
+        lead = [conform(prop1, 1, "property map 1"), conform(prop2, 1, "property map 2")]
+    maps, jobs = [], []
     for name, a, b in pairs:
         ch = max(a.shape[-3], b.shape[-3])
-        ta, tb = conform(a, ch, f"{name} (material1)"), conform(b, ch, f"{name} (material2)")
-        out = torch.empty(ta.shape, dtype=torch.float32, device=device)
         is_normal = name == "normal"
         if is_normal and ch != 3:
             raise ValueError("Normal maps must have 3 channels to be blended.")
         if ch > 4:
             raise ValueError(f"map '{name}' has {ch} channels; at most 4 are supported per map")
-        jobs.append((ta, tb, out, ch, is_normal))
-        outs[name] = out
-        keep.extend((ta, tb))
+        maps.extend((conform(a, ch, f"{name} (material1)"), conform(b, ch, f"{name} (material2)")))
+        jobs.append((name, ch, is_normal))
+    meta.jobs = jobs
 
-    with torch.cuda.device(device):
-        first = True
-        chunk = _cabi.PBR_MAX_BLEND_MAPS
-        for start in range(0, max(len(jobs), 1), chunk):
-            part = jobs[start : start + chunk]
-            d.n_maps = len(part)
-            for i, (ta, tb, out, ch, is_normal) in enumerate(part):
-                d.maps[i] = _cabi.PbrBlendMap(_cabi.plane(ta), _cabi.plane(tb), _cabi.plane(out), ch, int(is_normal))
-            d.normal_min = normal_min.data_ptr() if any(j[4] for j in part) else None
-            if not first:
-                d.mask_out = _cabi.PbrPlane(None, 0, 0, 0)  # already written by the first launch
-            _cabi.check(lib.pbr_blend(_cabi.byref(d), _cabi.stream_ptr(device)), "pbr_blend")
-            first = False
+    with_grad = torch.is_grad_enabled() and any(t.requires_grad for t in lead + maps)
+    if with_grad:
+        mask_out, normal_min, *outs = _BlendFn.apply(meta, len(lead), *lead, *maps)
+        if mode == _cabi.MASK_GIVEN:
+            mask_out = None
+    else:
+        mask_out, outs, normal_min = _blend_launch(meta, [t.detach() for t in lead], [t.detach() for t in maps])
+    outs = {job[0]: o for job, o in zip(jobs, outs)}
 
     # hand the maps to the new material the way `setattr(blended_material, name, map)` would
     blended.device = device
@@ -154,8 +264,14 @@ def _run_blend(material1: MaterialBase, material2: MaterialBase, mode: int, mask
             t = outs[name]
             if name == "normal":
                 # base.py:210-217 on the blended normal: min() < 0 -> keep, else remap *2-1 and renormalise
-                if not (float(normal_min.item()) < 0):
-                    t = _normal_ingest_cuda(t, 3)
+                if with_grad:
+                    # (the remap needs its own autograd node: decided on the host from the 4-byte probe result)
+                    if not (float(normal_min.item()) < 0):
+                        t = normal_ingest(t, 3)
+                else:
+                    # decided on the device: the remap kernel reads the probe result the blend kernel left there and
+                    # returns at once when it is negative - no read-back, the stream is never drained
+                    _normal_ingest_cuda(t, 3, out=t, cond_min=normal_min)
             blended._maps[name] = t
         else:
             setattr(blended, name, passthrough[name])

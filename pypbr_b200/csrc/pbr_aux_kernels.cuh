@@ -106,6 +106,43 @@ __global__ void __launch_bounds__(kThreads) index_transform_kernel(const __grid_
   const PbrIndexDesc& d = p.d;
   const Where w = locate(d.H_out, d.W_out, p.vec_ok != 0);
   if (!w.active) return;
+  const int ry = d.reduce_y > 1 ? d.reduce_y : 1, rx = d.reduce_x > 1 ? d.reduce_x : 1;
+  if (ry * rx > 1) {
+    // adjoint of a tile: every output texel sums the ry x rx source texels that were copies of it
+    for (int m = 0; m < d.n_maps; ++m) {
+      const PbrIndexMap& im = d.maps[m];
+      for (int c = 0; c < im.channels; ++c) {
+        const bool neg = (im.negate_mask >> c) & 1;
+        float v[kTexels];
+#pragma unroll
+        for (int i = 0; i < kTexels; ++i) v[i] = 0.0f;
+        for (int ty = 0; ty < ry; ++ty) {
+          int sy = d.origin_y + d.step_y * (w.row + ty * d.H_out);
+          bool row_in = true;
+          if (d.wrap) sy = wrap_index(sy, d.H_in);
+          else row_in = sy >= 0 && sy < d.H_in;
+          if (!row_in) continue;
+          const float* src = im.in.ptr + plane_off(im.in, w.b, c, sy, 0);
+          for (int tx = 0; tx < rx; ++tx) {
+#pragma unroll
+            for (int i = 0; i < kTexels; ++i) {
+              int x = d.origin_x + d.step_x * (w.col0 + i + tx * d.W_out);
+              bool in = true;
+              if (d.wrap) x = wrap_index(x, d.W_in);
+              else in = x >= 0 && x < d.W_in;
+              if (i < w.valid && in) v[i] += __ldg(src + x);
+            }
+          }
+        }
+        if (neg) {
+#pragma unroll
+          for (int i = 0; i < kTexels; ++i) v[i] = -v[i];
+        }
+        store_seg<kTexels>(im.out.ptr + plane_off(im.out, w.b, c, w.row, w.col0), w.vec, w.valid, v);
+      }
+    }
+    return;
+  }
   int sy = d.origin_y + d.step_y * w.row;
   bool row_in = true;
   if (d.wrap) sy = wrap_index(sy, d.H_in);

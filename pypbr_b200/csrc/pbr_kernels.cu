@@ -823,7 +823,9 @@ namespace pbr {
 // ------------------------------------------------------------------------------------------------
 struct ConvKParams {
   int B, H, W, vec_ok, albedo_is_srgb;
+  int met_channels;   // m2s: 1 or 3
   PbrPlane albedo, metspec, out0, out1;
+  PbrPlane g0, g1, d_albedo, d_metspec;   // backward
 };
 
 template <bool kM2S>
@@ -833,15 +835,17 @@ __global__ void __launch_bounds__(kThreads) convert_kernel(const __grid_constant
   float a[3][kTexels], m[3][kTexels], o0[3][kTexels], o1[3][kTexels];
 #pragma unroll
   for (int c = 0; c < 3; ++c) load_seg<kTexels>(p.albedo.ptr + plane_off(p.albedo, w.b, c, w.row, w.col0), w.vec, w.valid, a[c]);
-  constexpr int mc = kM2S ? 1 : 3;
+  const int mc = kM2S ? p.met_channels : 3;
 #pragma unroll
-  for (int c = 0; c < mc; ++c) load_seg<kTexels>(p.metspec.ptr + plane_off(p.metspec, w.b, c, w.row, w.col0), w.vec, w.valid, m[c]);
+  for (int c = 0; c < 3; ++c)
+    if (c < mc) load_seg<kTexels>(p.metspec.ptr + plane_off(p.metspec, w.b, c, w.row, w.col0), w.vec, w.valid, m[c]);
 #pragma unroll
   for (int i = 0; i < kTexels; ++i) {
     if (kM2S) {
       const float a3[3] = {a[0][i], a[1][i], a[2][i]};
+      const float m3[3] = {m[0][i], mc == 3 ? m[1][i] : m[0][i], mc == 3 ? m[2][i] : m[0][i]};
       float d3[3], s3[3];
-      convert_m2s(a3, m[0][i], p.albedo_is_srgb != 0, d3, s3);
+      convert_m2s(a3, m3, p.albedo_is_srgb != 0, d3, s3);
 #pragma unroll
       for (int c = 0; c < 3; ++c) { o0[c][i] = d3[c]; o1[c][i] = s3[c]; }
     } else {
@@ -975,6 +979,8 @@ struct NormalKParams {
   int B, H, W, vec_ok, channels;
   PbrPlane in, out;
   float* result;
+  const float* cond_min;   // ingest: skip the launch's work when *cond_min < 0 (PbrNormalDesc.cond_min)
+  PbrPlane g_out, d_in;    // backward
 };
 
 __global__ void __launch_bounds__(kThreads) normal_min_kernel(const __grid_constant__ NormalKParams p) {
@@ -993,6 +999,7 @@ __global__ void __launch_bounds__(kThreads) normal_min_kernel(const __grid_const
 __global__ void __launch_bounds__(kThreads) normal_ingest_kernel(const __grid_constant__ NormalKParams p) {
   const Where w = locate(p.H, p.W, p.vec_ok != 0);
   if (!w.active) return;
+  if (p.cond_min && __ldg(p.cond_min) < 0.0f) return;   // base.py:212: a map with a negative component is kept as it is
   float v[3][kTexels], o[3][kTexels];
   for (int c = 0; c < p.channels; ++c) load_seg<kTexels>(p.in.ptr + plane_off(p.in, w.b, c, w.row, w.col0), w.vec, w.valid, v[c]);
 #pragma unroll
@@ -1015,6 +1022,7 @@ __global__ void __launch_bounds__(kThreads) normal_ingest_kernel(const __grid_co
 }  // namespace pbr
 
 #include "pbr_aux_kernels.cuh"
+#include "pbr_grad_kernels.cuh"
 #endif   // PBR_MAIN_PART
 
 
@@ -1083,7 +1091,7 @@ static int fill_ct_params(const PbrCtDesc* d, CtKParams& k) {
 
 static int launch_result() {
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  cudaError_t e = cudaPeekAtLastError();
+  cudaError_t e = cudaGetLastError();   // this launch's own status: read AND cleared, so a failure is reported once, here
   return e == cudaSuccess ? PBR_OK : (int)e;
 }
 
@@ -1343,6 +1351,10 @@ uint64_t pbr_sizeof(int which) {
     case 13: return sizeof(PbrAdamDesc);
     case 14: return sizeof(PbrCtAdam);
     case 15: return sizeof(PbrNormalOpDesc);
+    case 16: return sizeof(PbrConvGrads);
+    case 17: return sizeof(PbrBlendGradMap);
+    case 18: return sizeof(PbrBlendGrads);
+    case 19: return sizeof(PbrNormalGrads);
     default: return 0;
   }
 }
@@ -1416,8 +1428,10 @@ static int run_convert(const PbrConvDesc* d, bool m2s, pbr_stream_t stream) {
   if (!d) return PBR_E_NULL;
   if (int rc = check_dims(d->B, d->H, d->W)) return rc;
   if (!d->albedo.ptr || !d->metspec.ptr || !d->out0.ptr || !d->out1.ptr) return PBR_E_NULL;
+  if (m2s && d->metallic_channels != 0 && d->metallic_channels != 1 && d->metallic_channels != 3) return PBR_E_CHANNELS;
   ConvKParams k{};
   k.B = d->B; k.H = d->H; k.W = d->W; k.albedo_is_srgb = d->albedo_is_srgb;
+  k.met_channels = d->metallic_channels == 3 ? 3 : 1;
   k.albedo = d->albedo; k.metspec = d->metspec; k.out0 = d->out0; k.out1 = d->out1;
   k.vec_ok = plane_vec_ok(d->albedo) && plane_vec_ok(d->metspec) && plane_vec_ok(d->out0) && plane_vec_ok(d->out1);
   dim3 grid, block;
@@ -1427,8 +1441,29 @@ static int run_convert(const PbrConvDesc* d, bool m2s, pbr_stream_t stream) {
   return launch_result();
 }
 
+static int run_convert_backward(const PbrConvDesc* d, const PbrConvGrads* g, bool m2s, pbr_stream_t stream) {
+  if (!d || !g) return PBR_E_NULL;
+  if (int rc = check_dims(d->B, d->H, d->W)) return rc;
+  if (!d->albedo.ptr || !d->metspec.ptr) return PBR_E_NULL;
+  if (m2s && d->metallic_channels != 0 && d->metallic_channels != 1 && d->metallic_channels != 3) return PBR_E_CHANNELS;
+  ConvKParams k{};
+  k.B = d->B; k.H = d->H; k.W = d->W; k.albedo_is_srgb = d->albedo_is_srgb;
+  k.met_channels = d->metallic_channels == 3 ? 3 : 1;
+  k.albedo = d->albedo; k.metspec = d->metspec;
+  k.g0 = g->g_out0; k.g1 = g->g_out1; k.d_albedo = g->d_albedo; k.d_metspec = g->d_metspec;
+  k.vec_ok = plane_vec_ok(d->albedo) && plane_vec_ok(d->metspec) && plane_vec_ok(g->g_out0) && plane_vec_ok(g->g_out1) &&
+             plane_vec_ok(g->d_albedo) && plane_vec_ok(g->d_metspec);
+  dim3 grid, block;
+  launch_shape(k.B, k.H, k.W, grid, block);
+  if (m2s) convert_bwd_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(k);
+  else convert_bwd_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(k);
+  return launch_result();
+}
+
 int pbr_convert_m2s(const PbrConvDesc* desc, pbr_stream_t stream) { return run_convert(desc, true, stream); }
 int pbr_convert_s2m(const PbrConvDesc* desc, pbr_stream_t stream) { return run_convert(desc, false, stream); }
+int pbr_convert_m2s_backward(const PbrConvDesc* desc, const PbrConvGrads* grads, pbr_stream_t stream) { return run_convert_backward(desc, grads, true, stream); }
+int pbr_convert_s2m_backward(const PbrConvDesc* desc, const PbrConvGrads* grads, pbr_stream_t stream) { return run_convert_backward(desc, grads, false, stream); }
 
 int pbr_blend(const PbrBlendDesc* d, pbr_stream_t stream) {
   if (!d) return PBR_E_NULL;
@@ -1455,6 +1490,32 @@ int pbr_blend(const PbrBlendDesc* d, pbr_stream_t stream) {
   dim3 grid, block;
   launch_shape(d->B, d->H, d->W, grid, block);
   blend_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);
+  return launch_result();
+}
+
+int pbr_blend_backward(const PbrBlendDesc* d, const PbrBlendGrads* g, pbr_stream_t stream) {
+  if (!d || !g) return PBR_E_NULL;
+  if (int rc = check_dims(d->B, d->H, d->W)) return rc;
+  if (d->n_maps < 0) return PBR_E_SHAPE;
+  if (d->n_maps > PBR_MAX_BLEND_MAPS) return PBR_E_TOO_MANY;
+  if (d->mask_mode < PBR_MASK_GIVEN || d->mask_mode > PBR_MASK_GRADIENT_V) return PBR_E_ENUM;
+  if (!g->mask.ptr) return PBR_E_NULL;
+  BlendBwdKParams k{};
+  k.d = *d;
+  k.g = *g;
+  bool vec = plane_vec_ok(g->mask) && plane_vec_ok(g->g_mask_out) && plane_vec_ok(g->d_mask) && plane_vec_ok(g->d_prop1) && plane_vec_ok(g->d_prop2);
+  for (int m = 0; m < d->n_maps; ++m) {
+    const PbrBlendMap& bm = d->maps[m];
+    if (!bm.a.ptr || !bm.b.ptr) return PBR_E_NULL;
+    if (bm.channels < 1 || bm.channels > 4 || (bm.is_normal && bm.channels != 3)) return PBR_E_CHANNELS;
+    vec = vec && plane_vec_ok(bm.a) && plane_vec_ok(bm.b) && plane_vec_ok(g->maps[m].g_out) && plane_vec_ok(g->maps[m].d_a) && plane_vec_ok(g->maps[m].d_b);
+  }
+  k.vec_ok = vec;
+  k.width_eps = d->blend_width + 1e-6f;
+  k.need_dmask = (d->mask_mode == PBR_MASK_GIVEN && g->d_mask.ptr) || (d->mask_mode == PBR_MASK_SIGMOID && (g->d_prop1.ptr || g->d_prop2.ptr));
+  dim3 grid, block;
+  launch_shape(d->B, d->H, d->W, grid, block);
+  blend_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);
   return launch_result();
 }
 
@@ -1498,9 +1559,23 @@ int pbr_normal_min(const PbrNormalDesc* d, float* result, pbr_stream_t stream) {
 int pbr_normal_ingest(const PbrNormalDesc* d, pbr_stream_t stream) {
   NormalKParams k{};
   if (int rc = fill_normal(d, k, true)) return rc;
+  if (d->channels == 2 && d->in.ptr == d->out.ptr) return PBR_E_NULL;   // 2 -> 3 channels cannot run in place
+  k.cond_min = d->cond_min;
   dim3 grid, block;
   launch_shape(k.B, k.H, k.W, grid, block);
   normal_ingest_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);
+  return launch_result();
+}
+
+int pbr_normal_ingest_backward(const PbrNormalDesc* d, const PbrNormalGrads* g, pbr_stream_t stream) {
+  NormalKParams k{};
+  if (int rc = fill_normal(d, k, false)) return rc;
+  if (!g || !g->g_out.ptr || !g->d_in.ptr) return PBR_E_NULL;
+  k.g_out = g->g_out; k.d_in = g->d_in;
+  k.vec_ok = k.vec_ok && plane_vec_ok(g->g_out) && plane_vec_ok(g->d_in);
+  dim3 grid, block;
+  launch_shape(k.B, k.H, k.W, grid, block);
+  normal_ingest_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);
   return launch_result();
 }
 
@@ -1540,6 +1615,7 @@ int pbr_index_transform(const PbrIndexDesc* d, pbr_stream_t stream) {
   if ((d->step_y != 1 && d->step_y != -1) || (d->step_x != 1 && d->step_x != -1)) return PBR_E_ENUM;
   if (d->n_maps < 0) return PBR_E_SHAPE;
   if (d->n_maps > PBR_MAX_INDEX_MAPS) return PBR_E_TOO_MANY;
+  if (d->reduce_y < 0 || d->reduce_x < 0 || d->reduce_y > 4096 || d->reduce_x > 4096) return PBR_E_SHAPE;
   IndexKParams k{};
   k.d = *d;
   bool vec = true;

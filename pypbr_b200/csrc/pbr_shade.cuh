@@ -13,8 +13,12 @@
 #ifndef PBR_P1_UNROLL
 #define PBR_P1_UNROLL 2
 #endif
+#ifndef PBR_BOUNDARY_RECOMPUTE
+#define PBR_BOUNDARY_RECOMPUTE 1   // one-pass accumulate backward: texels whose saved output sits at the clamp's upper end recompute the sum
+#endif
 namespace pbr {
 constexpr int kFwdUnroll = PBR_FWD_UNROLL, kP1Unroll = PBR_P1_UNROLL;
+constexpr bool kBoundaryRecompute = PBR_BOUNDARY_RECOMPUTE != 0;
 }
 #ifndef PBR_MAX_LIGHTS
 #define PBR_MAX_LIGHTS 64
@@ -154,6 +158,9 @@ PBR_HD void light_geom(const CtStage& S, int l, const V (&x)[N], float y, const 
   }
 }
 
+PBR_HD bool any_ge(float v, float t) { return v >= t; }
+PBR_HD bool any_ge(f2 v, float t) { return v.x >= t || v.y >= t; }
+
 template <class V>
 PBR_HD V encode_out(V c, bool return_srgb) { return return_srgb ? srgb_encode<false>(c, (V*)nullptr) : c; }
 template <class V>
@@ -250,9 +257,9 @@ struct NoSavedOut {
 
 // d encode(clamp(acc)) / d acc from out = encode(clamp(acc)) (utils/functions.py:50-66 inverted on its upper branch:
 // t^(1/2.4 - 1) = u^-1.4 with u = (out + 0.055)/1.055).  out >= encode(1) - which is 0.99999994, not 1, in fp32:
-// 1.055 - 0.055 rounds down, in the reference too - is read as "the sum was clamped": the one or two fp32 values of the
-// sum just below 1 that encode to the same number lose their gradient (the tolerant-zone rounding of the sum already
-// moves that boundary by more than this).
+// 1.055 - 0.055 rounds down, in the reference too - is read as "the sum was clamped" here; the caller recomputes the sum
+// for exactly those texels (kBoundaryRecompute), because a sum of exactly 1 (torch.clamp's gate is inclusive) and the one
+// or two fp32 sums just below it encode to the same number.
 template <class V>
 PBR_HD V encode_slope_from_out(V out, bool return_srgb) {
   V slope = splat<V>(1.0f);
@@ -296,45 +303,56 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
   const bool two_pass = (!F.per_light) && L > 1;
   V g_tot[3][N];  // two-pass only: gradient w.r.t. every per-light colour
   fetch(0);
-  if (two_pass && saved_out.have()) {
-    // single pass: gate and slope of encode(clamp(sum)) from the forward launch's output
-    V outv[3][N];
-    saved_out(outv);
-    fetch(L);
-    gout(0, outv, g_tot);
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int i = 0; i < N; ++i) g_tot[c][i] *= encode_slope_from_out(outv[c][i], F.return_srgb);
-  } else if (two_pass) {
-    // pass 1: the accumulated image, to know where clamp(sum) gates and the slope of the encode
-    V acc[3][N];
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int i = 0; i < N; ++i) acc[c][i] = splat<V>(0.0f);
-#pragma unroll kP1Unroll
-    for (int l = 0; l < L; ++l) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        LightGeomT<V> g;
-        light_geom<kLight, V, N>(S, l, x, y, hoisted, i, gc, g);
-        LightFwd<V> f;
-        V col[3];
-        shade_light_fwd<kWorkflow>(t[i], g, S.light[l].inten, f, col);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) acc[c][i] = xadd(acc[c][i], col[c]);
-      }
-    }
+  if (two_pass) {
+    // The gate of clamp(sum) and the slope of the encode.  With the forward launch's output at hand both are read off it
+    // (single pass) - except where that output sits at the clamp's upper end: encode(1) is also what a sum above 1 and
+    // the one or two fp32 sums just below 1 produce, and torch.clamp passes the gradient AT 1 (inclusive), so those
+    // texels - and only those - recompute the summed image like the two-pass path (PBR_BOUNDARY_RECOMPUTE).
     V outv[3][N], slope[3][N];
+    bool recompute = true;
+    if (saved_out.have()) {
+      saved_out(outv);
+      recompute = false;
+      const float top = F.return_srgb ? srgb_encode<false, float>(1.0f, nullptr) : 1.0f;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+      for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        const V cl = clamp01(acc[c][i]);
-        outv[c][i] = encode_out_d(cl, F.return_srgb, &slope[c][i]);
-        slope[c][i] = gated(slope[c][i], acc[c][i], cl);
+        for (int i = 0; i < N; ++i) {
+          slope[c][i] = encode_slope_from_out(outv[c][i], F.return_srgb);
+          if (kBoundaryRecompute) recompute = recompute || any_ge(outv[c][i], top);
+        }
+    }
+    if (recompute) {
+      // pass 1: the accumulated image, to know where clamp(sum) gates and the slope of the encode
+      V acc[3][N];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[c][i] = splat<V>(0.0f);
+#pragma unroll kP1Unroll
+      for (int l = 0; l < L; ++l) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          LightGeomT<V> g;
+          light_geom<kLight, V, N>(S, l, x, y, hoisted, i, gc, g);
+          LightFwd<V> f;
+          V col[3];
+          shade_light_fwd<kWorkflow>(t[i], g, S.light[l].inten, f, col);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[c][i] = xadd(acc[c][i], col[c]);
+        }
       }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const V cl = clamp01(acc[c][i]);
+          V sl;
+          const V o = encode_out_d(cl, F.return_srgb, &sl);
+          if (!saved_out.have()) outv[c][i] = o;
+          slope[c][i] = gated(sl, acc[c][i], cl);
+        }
+    }
     fetch(L);   // rotate: the buffer requested before pass 1 becomes current
     gout(0, outv, g_tot);
 #pragma unroll

@@ -47,6 +47,8 @@ def fused_loss_step(
     want_intensity_grad: bool = False,
     out: Optional[Dict[str, torch.Tensor]] = None,
     want_geometry_grad: bool = False,
+    want_map_grads: bool = True,
+    device=None,
 ):
     """
     One fused forward + MSE + backward pass over a (batched) material.
@@ -57,12 +59,15 @@ def fused_loss_step(
          (keys d_albedo, d_normal, d_roughness, d_metspec, buf).
     want_geometry_grad: also the gradients of the light positions / directions and of the view direction (shared
          parameters of a fit with unknown lighting); buf then has 1 + 6L + 3 floats.
+    want_map_grads: False -> loss (and shared-parameter gradients) only: no gradient buffer is allocated or written.
+    device: where to shade (default material.device; maps living elsewhere are moved, like CookTorranceBRDF's override_device).
     Returns (buf, grads): buf is a device tensor [loss_sum, d_intensity(L*3)..., (d_lights(L*3)..., d_view(3))]
     (loss_sum is the UNscaled sum of squared errors; multiply by loss_scale for the mean), grads a dict of tensors.
     """
     lib = _cabi.load()
     cfg, (albedo, normal, roughness, metspec), _leaf, device = _prepare(
-        material, material.device, view_dir, lights, intensity, light_type, light_size, return_srgb, multi_light
+        material, device if device is not None else material.device, view_dir, lights, intensity, light_type, light_size,
+        return_srgb, multi_light
     )
     _cabi.require_cuda(target, "target")
     target = target.contiguous()
@@ -83,10 +88,10 @@ def fused_loss_step(
     keep: list = []
     d = _fill_desc(cfg, albedo, normal, roughness, metspec, keep)
     g = _cabi.PbrCtGrads()
-    d_albedo = buf("d_albedo", albedo)
-    d_normal = buf("d_normal", normal) if normal is not None else None
-    d_rough = buf("d_roughness", roughness)
-    d_met = buf("d_metspec", metspec)
+    d_albedo = buf("d_albedo", albedo) if want_map_grads else None
+    d_normal = buf("d_normal", normal) if (normal is not None and want_map_grads) else None
+    d_rough = buf("d_roughness", roughness) if want_map_grads else None
+    d_met = buf("d_metspec", metspec) if want_map_grads else None
     g.d_albedo, g.d_normal = _cabi.plane(d_albedo), _cabi.plane(d_normal)
     g.d_roughness, g.d_metspec = _cabi.plane(d_rough), _cabi.plane(d_met)
     red = out.get("buf")
@@ -117,13 +122,85 @@ def allreduce_loss_and_shared(buf: torch.Tensor, group=None) -> torch.Tensor:
     """
     The ONLY collective of the sharded fit: SUM all-reduce of [loss_sum, d_intensity...] (1 + 3L floats)
     over NCCL / NVLink.  Per-material map gradients are never communicated.  No-op without an
-    initialised process group (single GPU).
+    initialised process group (single GPU).  Issued on the current stream: whatever is launched next waits for it.
     """
     import torch.distributed as dist
 
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     return buf
+
+
+class PendingLoss:
+    """
+    Handle of a loss all-reduce that was issued OFF the compute stream (`allreduce_loss_async`).  The update of a
+    `fit_step(..., fused=True)` does not depend on the reduced loss (its gradient scale 1/global_numel is known up
+    front), so the next step's kernel must not wait for the slowest rank's previous step: the collective runs on a side
+    stream behind an event and only whoever reads the loss waits for it.
+
+    wait()  : the CURRENT stream waits for the all-reduce; returns the reduced device buffer.
+    item()  : host-synchronises on the all-reduce only (not on the compute stream) and returns buf[0] * scale.
+    """
+
+    def __init__(self, buf: torch.Tensor, work=None, done: Optional["torch.cuda.Event"] = None, scale: float = 1.0):
+        self.buf, self._work, self._done, self.scale = buf, work, done, scale
+
+    def wait(self) -> torch.Tensor:
+        if self._done is not None:
+            torch.cuda.current_stream(self.buf.device).wait_event(self._done)
+        elif self._work is not None:   # CPU group (gloo): the work object blocks the host
+            self._work.wait()
+            self._work = None
+        return self.buf
+
+    def item(self) -> float:
+        if self._done is not None:
+            self._done.synchronize()
+        elif self._work is not None:
+            self._work.wait()
+            self._work = None
+        elif self.buf.is_cuda:
+            torch.cuda.current_stream(self.buf.device).synchronize()
+        return float(self.buf[0]) * self.scale
+
+
+_side_streams: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(device: torch.device) -> "torch.cuda.Stream":
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _side_streams.get(idx)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _side_streams[idx] = st
+    return st
+
+
+def allreduce_loss_async(buf: torch.Tensor, group=None, scale: float = 1.0, timing: Optional[list] = None) -> PendingLoss:
+    """
+    `allreduce_loss_and_shared` off the compute stream: a side stream waits (event) for what the compute stream has
+    enqueued so far - the kernel that fills `buf` - and carries the collective; the compute stream goes on at once.
+    The caller must not touch `buf` on the compute stream before `PendingLoss.wait()` (fit_step alternates two buffers).
+    timing: optional list that receives a (start, end) CUDA-event pair bracketing the collective on the side stream.
+    """
+    import torch.distributed as dist
+
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if not buf.is_cuda:   # CPU tensors (gloo tests): plain asynchronous work object
+        return PendingLoss(buf, dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group, async_op=True) if multi else None, None, scale)
+    side = _side_stream(buf.device)
+    side.wait_stream(torch.cuda.current_stream(buf.device))
+    done = torch.cuda.Event(enable_timing=timing is not None)
+    with torch.cuda.stream(side):
+        if timing is not None:
+            t0 = torch.cuda.Event(enable_timing=True)
+            t0.record(side)
+        if multi:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group, async_op=True).wait()   # side stream waits, not the host
+        done.record(side)
+        if timing is not None:
+            timing.append((t0, done))
+    return PendingLoss(buf, None, done, scale)
 
 
 # projection that keeps a fitted map valid after every optimiser step
@@ -196,6 +273,7 @@ class FusedAdam:
             device = t.device
         with torch.cuda.device(device):
             _cabi.check(lib.pbr_adam_step(_cabi.byref(d), _cabi.stream_ptr(device)), "pbr_adam_step")
+        _cabi.touch(*self.params.values())
         self.step_count = t_step
 
 
@@ -281,6 +359,7 @@ def fused_fit_step(
             lib.pbr_ct_fit_step(_cabi.byref(d), _cabi.byref(ls), _cabi.byref(a), d_int, _cabi.stream_ptr(device)),
             "pbr_ct_fit_step",
         )
+    _cabi.touch(*optimizer.params.values())
     optimizer.step_count = t
     return red
 
@@ -288,19 +367,34 @@ def fused_fit_step(
 def fit_step(material: MaterialBase, optimizer: FusedAdam, target: torch.Tensor, view_dir, lights, intensity,
              light_type: str = "point", light_size: Optional[float] = None, multi_light: str = "per_light",
              scratch: Optional[Dict[str, torch.Tensor]] = None, global_numel: Optional[int] = None,
-             fused: bool = False) -> torch.Tensor:
+             fused: bool = False, async_loss: bool = False, timing: Optional[list] = None):
     """
     One step of the sharded inverse-rendering fit on this rank's materials: fused render + MSE + backward
     (pbr_ct_loss_fwd_bwd), ONE all-reduce of the loss buffer, fused Adam + projection (pbr_adam_step).
     `fused=True`: all of it in one launch (pbr_ct_fit_step, see fused_fit_step); the all-reduce then only serves
-    the reported loss.
+    the reported loss.  With `async_loss=True` it therefore leaves the compute stream (allreduce_loss_async) and the
+    call returns a PendingLoss; the loss buffers alternate between two slots of `scratch`, and a slot is only reused
+    after its all-reduce of two steps ago has completed.
     `global_numel`: element count of the target over ALL ranks (the MSE denominator); default: this rank's.
-    Returns the all-reduced buffer [sum of squared errors, ...] (device tensor; multiply [0] by 1/global_numel).
+    Returns the all-reduced buffer [sum of squared errors, ...] (device tensor; multiply [0] by 1/global_numel), or
+    the PendingLoss that will deliver it.
     """
     numel = global_numel if global_numel is not None else target.numel()
     if fused:
+        if async_loss:
+            scratch = scratch if scratch is not None else {}
+            ring = scratch.setdefault("loss_ring", [None, None])
+            pend = scratch.setdefault("loss_pending", [None, None])
+            i = scratch["loss_slot"] = 1 - scratch.get("loss_slot", 1)
+            if pend[i] is not None:
+                pend[i].wait()   # stream-level: the all-reduce of two steps ago, long finished
+            scratch["buf"] = ring[i]
         buf = fused_fit_step(material, optimizer, target, view_dir, lights, intensity, light_type, light_size,
                              multi_light=multi_light, loss_scale=1.0 / numel, scratch=scratch)
+        if async_loss:
+            ring[i] = buf
+            pend[i] = allreduce_loss_async(buf, scale=1.0 / numel, timing=timing)
+            return pend[i]
         return allreduce_loss_and_shared(buf)
     buf, grads = fused_loss_step(material, target, view_dir, lights, intensity, light_type, light_size,
                                  multi_light=multi_light, loss_scale=1.0 / numel, out=scratch)
@@ -337,18 +431,42 @@ class RenderingLoss(nn.Module):
         names = [k for k in ("albedo", "normal", "roughness", "metallic", "specular")
                  if predicted_material._maps.get(k) is not None]
         leaves = [predicted_material._maps[k] for k in names]
-        kw = dict(light_type=self.light_type, light_size=self.light_size, multi_light="per_light")
+        shared = [t if isinstance(t, torch.Tensor) else torch.as_tensor(t, dtype=torch.float32)
+                  for t in (self.light_intensity, self.light_dir, self.view_dir)]
+        grad_on = torch.is_grad_enabled()
+        want_maps = grad_on and any(t.requires_grad for t in leaves)
+        want_int = grad_on and shared[0].requires_grad
+        want_geo = grad_on and (shared[1].requires_grad or shared[2].requires_grad)
+        kw = dict(light_type=self.light_type, light_size=self.light_size, multi_light="per_light",
+                  want_map_grads=want_maps, want_intensity_grad=want_int, want_geometry_grad=want_geo,
+                  device=self.brdf.override_device)
+        L = shared[1].shape[0] if shared[1].dim() == 2 else 1
 
         class _Fn(torch.autograd.Function):
             @staticmethod
-            def forward(ctx, *ls):
-                red, grads = fused_loss_step(predicted_material, target, self.view_dir, self.light_dir,
-                                             self.light_intensity, **kw)
-                ctx.grads = [grads.get(k) for k in names]
+            def forward(ctx, *inputs):
+                red, grads = fused_loss_step(predicted_material, target, shared[2], shared[1], shared[0], **kw)
+                # gradients come back in the shape the kernel shaded ((1,H,W) for an (H,W) map, a broadcast map expanded to
+                # the batch): reduce them onto the leaves' own shapes
+                ctx.grads = [grads[k].sum_to_size(t.shape) if (want_maps and grads.get(k) is not None) else None
+                             for k, t in zip(names, leaves)]
+                red = red.detach()
+                g_int = red[1:1 + 3 * L].view(L, 3) if want_int else None
+                g_light = red[1 + 3 * L:1 + 6 * L].view(L, 3) if want_geo else None
+                g_view = red[1 + 6 * L:1 + 6 * L + 3] if want_geo else None
+                def onto(g, t):   # (L,3) rows onto a (3,) or (L,3) leaf; (3,) onto any 3-element view tensor
+                    if g is None:
+                        return None
+                    g = g.reshape(t.shape) if g.numel() == t.numel() else g.sum_to_size(t.shape)
+                    return g.to(t.device)
+
+                ctx.shared = [onto(g, t) for g, t in zip((g_int, g_light, g_view), shared)]
                 return red[0] / target.numel()
 
             @staticmethod
             def backward(ctx, g):
-                return tuple((gr * g if gr is not None else None) for gr in ctx.grads)
+                maps = tuple((gr * g if gr is not None else None) for gr in ctx.grads)
+                sh = tuple((gr * g.to(gr.device) if gr is not None else None) for gr in ctx.shared)
+                return maps + sh
 
-        return _Fn.apply(*leaves)
+        return _Fn.apply(*leaves, *shared)

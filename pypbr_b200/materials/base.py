@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import copy
 import math
+import weakref
 from typing import Dict, List, Optional, Tuple, Union
 
 import numpy as np
@@ -147,7 +148,7 @@ class MaterialBase:
         if normal_map.is_cuda:
             if _normal_min_cuda(normal_map) < 0:
                 return normal_map
-            return _normal_ingest_cuda(normal_map, 3)
+            return normal_ingest(normal_map, 3)
         if normal_map.min() < 0:
             return normal_map
         return F.normalize(normal_map * 2.0 - 1.0, dim=_channel_dim(normal_map))
@@ -155,7 +156,7 @@ class MaterialBase:
     def _compute_normal_map_z_component(self, normal_xy: torch.Tensor) -> torch.Tensor:
         """base.py:223-242: xy in [0,1] -> [-1,1], z = sqrt(clamp(1 - x^2 - y^2, 1e-6)), normalise."""
         if normal_xy.is_cuda:
-            return _normal_ingest_cuda(normal_xy, 2)
+            return normal_ingest(normal_xy, 2)
         cd = _channel_dim(normal_xy)
         xy = normal_xy * 2 - 1
         x, y = xy.narrow(cd, 0, 1), xy.narrow(cd, 1, 1)
@@ -307,13 +308,15 @@ class MaterialBase:
     def tile(self, num_tiles: int):
         """Repeat every map num_tiles x num_tiles (base.py:521-537: tensor.repeat)."""
         if self._all_cuda():
-            return self._index_transform(lambda H, W: (H * num_tiles, W * num_tiles, 0, 1, 0, 1, True))
+            return self._index_transform(lambda H, W: (H * num_tiles, W * num_tiles, 0, 1, 0, 1, True),
+                                         adjoint=lambda H, W: (H, W, 0, 1, 0, 1, False, num_tiles, num_tiles))
         return self._each(lambda _n, t: t.repeat(*([1] * (t.dim() - 2)), num_tiles, num_tiles))
 
     def flip_horizontal(self):
         """Mirror along W; the normal's X component changes sign (base.py:605-621)."""
         if self._all_cuda():
-            return self._index_transform(lambda H, W: (H, W, 0, 1, W - 1, -1, False), negate={"normal": 0b001})
+            return self._index_transform(lambda H, W: (H, W, 0, 1, W - 1, -1, False), negate={"normal": 0b001},
+                                         adjoint=lambda H, W: (H, W, 0, 1, W - 1, -1, False, 0, 0))
 
         def f(name, t):
             out = t.flip(-1)
@@ -327,7 +330,8 @@ class MaterialBase:
     def flip_vertical(self):
         """Mirror along H; the normal's Y component changes sign (base.py:623-639)."""
         if self._all_cuda():
-            return self._index_transform(lambda H, W: (H, W, H - 1, -1, 0, 1, False), negate={"normal": 0b010})
+            return self._index_transform(lambda H, W: (H, W, H - 1, -1, 0, 1, False), negate={"normal": 0b010},
+                                         adjoint=lambda H, W: (H, W, H - 1, -1, 0, 1, False, 0, 0))
 
         def f(name, t):
             out = t.flip(-2)
@@ -341,7 +345,8 @@ class MaterialBase:
     def roll(self, shift: Tuple[int, int]):
         """torch.roll(map, shift, dims=(H, W)) on every map (base.py:641-655)."""
         if self._all_cuda():
-            return self._index_transform(lambda H, W: (H, W, (-int(shift[0])) % H, 1, (-int(shift[1])) % W, 1, True))
+            return self._index_transform(lambda H, W: (H, W, (-int(shift[0])) % H, 1, (-int(shift[1])) % W, 1, True),
+                                         adjoint=lambda H, W: (H, W, int(shift[0]) % H, 1, int(shift[1]) % W, 1, True, 0, 0))
         return self._each(lambda _n, t: torch.roll(t, shift, dims=(-2, -1)))
 
     # -- CUDA path of the index transforms: every map of the material in ONE gather kernel (pbr_index_transform)
@@ -349,13 +354,15 @@ class MaterialBase:
         ts = [t for t in self._maps.values() if t is not None]
         return bool(ts) and all(t.is_cuda and t.dtype == torch.float32 for t in ts)
 
-    def _index_transform(self, geometry, negate: Optional[Dict[str, int]] = None):
+    def _index_transform(self, geometry, negate: Optional[Dict[str, int]] = None, adjoint=None):
         """
         geometry(H_in, W_in) -> (H_out, W_out, origin_y, step_y, origin_x, step_x, wrap).  Maps that share
         (batch, H, W) travel in one launch; results are bit-identical to the torch calls of the reference
         (pure data movement; the sign flip of a normal component is exact).
+        adjoint(H_in, W_in) -> the same tuple + (reduce_y, reduce_x) describing the transposed gather (gradient w.r.t.
+        the input from the gradient w.r.t. the output): maps that require grad go through an autograd.Function whose
+        backward is that launch, so flip / roll / tile stay differentiable like the reference's tensor.flip / roll / repeat.
         """
-        lib = _cabi.load()
         negate = negate or {}
         groups: Dict[tuple, list] = {}
         for name, t in self._maps.items():
@@ -366,24 +373,19 @@ class MaterialBase:
             key = (t.shape[0] if t.dim() == 4 else 1, t.dim(), t.shape[-2], t.shape[-1], t.device)
             groups.setdefault(key, []).append(name)
         for (B, _dim, H, W, device), names in groups.items():
-            H_out, W_out, oy, sy, ox, sx, wrap = geometry(H, W)
+            fwd = (*geometry(H, W), 0, 0)
             for start in range(0, len(names), _cabi.PBR_MAX_INDEX_MAPS):
                 part = names[start : start + _cabi.PBR_MAX_INDEX_MAPS]
-                d = _cabi.PbrIndexDesc()
-                d.B, d.H_in, d.W_in, d.H_out, d.W_out = B, H, W, H_out, W_out
-                d.origin_y, d.step_y, d.origin_x, d.step_x, d.wrap = oy, sy, ox, sx, int(wrap)
-                d.n_maps = len(part)
-                keep, outs = [], {}
-                for i, name in enumerate(part):
-                    src = _cabi.rowmajor(self._maps[name].detach())
-                    out = torch.empty(*src.shape[:-2], H_out, W_out, dtype=torch.float32, device=device)
-                    d.maps[i] = _cabi.PbrIndexMap(_cabi.plane(src), _cabi.plane(out), src.shape[-3], int(negate.get(name, 0)))
-                    keep.append(src)
-                    outs[name] = out
-                with torch.cuda.device(device):
-                    _cabi.check(lib.pbr_index_transform(_cabi.byref(d), _cabi.stream_ptr(device)), "pbr_index_transform")
-                for name, out in outs.items():
-                    self._maps[name] = out
+                srcs = [self._maps[n] for n in part]
+                negs = [int(negate.get(n, 0)) for n in part]
+                if torch.is_grad_enabled() and any(t.requires_grad for t in srcs):
+                    if adjoint is None:
+                        raise RuntimeError("pypbr_b200: this index transform has no adjoint; detach the maps first")
+                    outs = _IndexFn.apply((H, W), fwd, (*adjoint(H, W),), tuple(negs), *srcs)
+                else:
+                    outs = _index_launch([t.detach() for t in srcs], (H, W), fwd, negs)
+                for n, out in zip(part, outs):
+                    self._maps[n] = out
         return self
 
     def apply_transform(self, transform):
@@ -430,9 +432,27 @@ class MaterialBase:
         return self
 
     def adjust_normal_strength(self, strength_factor: float):
+        """
+        pypbr/materials/base.py:689-706: scale the normal's x / y by `strength_factor`, renormalise.  On CUDA maps the scale and
+        the normalisation are one pbr_normal_op launch (ROTATE with cos = strength_factor, sin = 0: x*f - y*0 and x*0 + y*f are
+        exactly RN(x*f), RN(y*f)).  The reference also scales the x / y of the ORIGINAL tensor in place (`normal[:2] *= f`, visible
+        to every material that aliases it); that side effect is kept.
+        """
         if self.normal is not None:
             normal = self.normal
             cd = _channel_dim(normal)
+            if normal.is_cuda and normal.dtype == torch.float32:
+                if torch.is_grad_enabled() and normal.requires_grad:
+                    raise RuntimeError("pypbr_b200: adjust_normal_strength scales the map in place and has no adjoint kernel; "
+                                       "detach the normal map first")
+                from ..utils.functions import _normal_op
+
+                src = _cabi.rowmajor(normal.detach())
+                out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+                _normal_op(src, out, _cabi.NORMAL_OP_ROTATE, cos_a=float(strength_factor), sin_a=0.0)
+                normal.narrow(cd, 0, 2).mul_(strength_factor)
+                self._maps["normal"] = out
+                return self
             normal.narrow(cd, 0, 2).mul_(strength_factor)
             self._maps["normal"] = F.normalize(normal, dim=cd)
         return self
@@ -526,24 +546,118 @@ def _normal_desc(t: torch.Tensor, out: Optional[torch.Tensor], channels: int) ->
     return _cabi.PbrNormalDesc(B, src.shape[-2], src.shape[-1], channels, _cabi.plane(src), _cabi.plane(out)), src
 
 
+# min() of a normal map that has already been probed, keyed by tensor identity and guarded by its version counter, so
+# that handing the same map to another material (every conversion does: metallic.py:112-118 passes normal=self.normal
+# through the constructor, which re-runs base.py:210-217) costs neither a reduction nor a device->host read-back.
+# In-place writers that bypass torch's version counter (the kernels' in-place entry points) bump it: _cabi.touch().
+_PROBED: Dict[int, tuple] = {}
+
+
 def _normal_min_cuda(t: torch.Tensor) -> float:
-    """The `normal_map.min() < 0` probe of base.py:212 as one reduction kernel + one 4-byte readback."""
+    """The `normal_map.min() < 0` probe of base.py:212 as one reduction kernel + one 4-byte readback (memoised)."""
     _cabi.require_cuda(t, "normal")
+    hit = _PROBED.get(id(t))
+    if hit is not None and hit[0]() is t and hit[1] == t._version:
+        return hit[2]
     lib = _cabi.load()
     res = torch.full((1,), float("inf"), dtype=torch.float32, device=t.device)
     d, _keep = _normal_desc(t.detach(), None, t.shape[_channel_dim(t)])
     with torch.cuda.device(t.device):
         _cabi.check(lib.pbr_normal_min(_cabi.byref(d), res.data_ptr(), _cabi.stream_ptr(t.device)), "pbr_normal_min")
-    return float(res.item())
+    value = float(res.item())
+    key = id(t)
+    _PROBED[key] = (weakref.ref(t, lambda _r, k=key: _PROBED.pop(k, None)), t._version, value)
+    return value
 
 
-def _normal_ingest_cuda(t: torch.Tensor, channels: int) -> torch.Tensor:
+def _normal_ingest_cuda(t: torch.Tensor, channels: int, out: Optional[torch.Tensor] = None,
+                        cond_min: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """pbr_normal_ingest.  out: write there (out is t: in place, 3 channels only).  cond_min: DEVICE scalar; the launch
+    leaves the map alone when it is negative (base.py:212 decided on the device, no read-back)."""
     _cabi.require_cuda(t, "normal")
     lib = _cabi.load()
-    shape = list(t.shape)
-    shape[_channel_dim(t)] = 3
-    out = torch.empty(shape, dtype=torch.float32, device=t.device)
+    if out is None:
+        shape = list(t.shape)
+        shape[_channel_dim(t)] = 3
+        out = torch.empty(shape, dtype=torch.float32, device=t.device)
     d, _keep = _normal_desc(t.detach(), out, channels)
+    if cond_min is not None:
+        d.cond_min = cond_min.data_ptr()
     with torch.cuda.device(t.device):
         _cabi.check(lib.pbr_normal_ingest(_cabi.byref(d), _cabi.stream_ptr(t.device)), "pbr_normal_ingest")
     return out
+
+
+class _NormalIngestFn(torch.autograd.Function):
+    """normalize(n*2-1) / the 2-channel z reconstruction with their adjoint kernel (base.py:215-217, :235-242 are
+    differentiable torch ops in the reference)."""
+
+    @staticmethod
+    def forward(ctx, t, channels: int):
+        src = _cabi.rowmajor(t.detach())
+        ctx.save_for_backward(src)
+        ctx.channels = channels
+        return _normal_ingest_cuda(src, channels)
+
+    @staticmethod
+    def backward(ctx, g):
+        (src,) = ctx.saved_tensors
+        lib = _cabi.load()
+        g = _cabi.rowmajor(g)
+        d_in = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+        d, _keep = _normal_desc(src, None, ctx.channels)
+        gr = _cabi.PbrNormalGrads(_cabi.plane(g), _cabi.plane(d_in))
+        with torch.cuda.device(src.device):
+            _cabi.check(lib.pbr_normal_ingest_backward(_cabi.byref(d), _cabi.byref(gr), _cabi.stream_ptr(src.device)),
+                        "pbr_normal_ingest_backward")
+        return d_in, None
+
+
+def normal_ingest(t: torch.Tensor, channels: int) -> torch.Tensor:
+    if torch.is_grad_enabled() and t.requires_grad:
+        return _NormalIngestFn.apply(t, channels)
+    return _normal_ingest_cuda(t, channels)
+
+
+# ---------------------------------------------------------------------- CUDA index transforms
+def _index_launch(srcs, size, geom, negs):
+    """One pbr_index_transform launch over maps that share (batch, H, W).  geom = (H_out, W_out, origin_y, step_y,
+    origin_x, step_x, wrap, reduce_y, reduce_x)."""
+    lib = _cabi.load()
+    H, W = size
+    H_out, W_out, oy, sy, ox, sx, wrap, ry, rx = geom
+    first = srcs[0]
+    d = _cabi.PbrIndexDesc()
+    d.B = first.shape[0] if first.dim() == 4 else 1
+    d.H_in, d.W_in, d.H_out, d.W_out = H, W, H_out, W_out
+    d.origin_y, d.step_y, d.origin_x, d.step_x, d.wrap = oy, sy, ox, sx, int(wrap)
+    d.reduce_y, d.reduce_x = ry, rx
+    d.n_maps = len(srcs)
+    keep, outs = [], []
+    for i, t in enumerate(srcs):
+        src = _cabi.rowmajor(t)
+        out = torch.empty(*src.shape[:-2], H_out, W_out, dtype=torch.float32, device=src.device)
+        d.maps[i] = _cabi.PbrIndexMap(_cabi.plane(src), _cabi.plane(out), src.shape[-3], negs[i])
+        keep.append(src)
+        outs.append(out)
+    with torch.cuda.device(first.device):
+        _cabi.check(lib.pbr_index_transform(_cabi.byref(d), _cabi.stream_ptr(first.device)), "pbr_index_transform")
+    return outs
+
+
+class _IndexFn(torch.autograd.Function):
+    """flip / roll / tile of several maps in one gather; the backward is the transposed gather, one launch as well."""
+
+    @staticmethod
+    def forward(ctx, size, fwd, adj, negs, *srcs):
+        ctx.size, ctx.adj, ctx.negs = size, adj, negs
+        ctx.out_size = (fwd[0], fwd[1])
+        ctx.metas = [(t.shape, t.device) for t in srcs]
+        return tuple(_index_launch([t.detach() for t in srcs], size, fwd, list(negs)))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        gs = [g if g is not None else torch.zeros(*shape[:-2], *ctx.out_size, dtype=torch.float32, device=dev)
+              for g, (shape, dev) in zip(gs, ctx.metas)]
+        outs = _index_launch(gs, ctx.out_size, ctx.adj, list(ctx.negs))
+        return (None, None, None, None, *outs)

@@ -252,6 +252,9 @@ def _prepare(material: MaterialBase, device, view_dir, light, intensity, light_t
     shared_leaves = (inten if inten.requires_grad else None,
                      lights if lights.requires_grad else None,
                      view if view.requires_grad else None)
+    # compare with the device the maps actually live on: torch.device("cuda") (no index) never equals "cuda:0", and the
+    # device-resident fast path (no .tolist() sync, graph-capturable) would be dead for material.to("cuda")
+    device = albedo.device
     all_dev = all(t.is_cuda and t.device == device for t in (view, lights, inten))
     cfg.on_device = all_dev
     if all_dev:

@@ -89,12 +89,19 @@ def rotate_normals(normal_map: torch.Tensor, angle: float) -> torch.Tensor:
     _cabi.require_cuda(normal_map, "normal_map")
     if normal_map.dim() not in (3, 4) or normal_map.shape[-3] != 3:
         raise ValueError(f"normal_map must have shape (3, H, W) or (B, 3, H, W), got {tuple(normal_map.shape)}")
+    if torch.is_grad_enabled() and normal_map.requires_grad:
+        # the reference assigns into normal_map[0..2] in place (utils/functions.py:104-106), which autograd refuses on a
+        # leaf that requires grad; this kernel has no adjoint, so the call is refused for any such tensor instead of
+        # silently cutting the graph
+        raise RuntimeError("pypbr_b200: rotate_normals works in place and is not differentiable; pass normal_map.detach()")
     theta = math.radians(angle)
     target = normal_map.detach()
     work = _cabi.rowmajor(target)
     _normal_op(work, work, _cabi.NORMAL_OP_ROTATE, cos_a=math.cos(theta), sin_a=math.sin(theta))
     if work.data_ptr() != target.data_ptr():   # W-strided view: the kernel worked on a packed copy
         target.copy_(work)
+    else:
+        _cabi.touch(normal_map)
     return normal_map
 
 
@@ -121,6 +128,8 @@ def compute_normal_from_height(height_map: torch.Tensor, scale: float = 1.0,
         height_map = height_map.unsqueeze(0)
     if height_map.dim() not in (3, 4) or height_map.shape[-3] != 1:
         raise ValueError(f"height_map must have shape (H, W), (1, H, W) or (B, 1, H, W), got {tuple(height_map.shape)}")
+    if torch.is_grad_enabled() and height_map.requires_grad:
+        raise RuntimeError("pypbr_b200: compute_normal_from_height has no adjoint kernel; pass height_map.detach()")
     src = _cabi.rowmajor(height_map.detach())
     shape = list(src.shape)
     shape[-3] = 3
@@ -145,6 +154,8 @@ def compute_height_from_normal(normal_map: torch.Tensor, scale: float = 1.0,
     if convention not in (NormalConvention.OPENGL, NormalConvention.DIRECTX):
         raise ValueError("Unsupported normal convention.")
     _cabi.require_cuda(normal_map, "normal_map")
+    if torch.is_grad_enabled() and normal_map.requires_grad:
+        raise RuntimeError("pypbr_b200: compute_height_from_normal has no adjoint kernel; pass normal_map.detach()")
     src = _cabi.rowmajor(normal_map.detach())
     H, W = src.shape[-2:]
     div = torch.empty((1, H, W), dtype=torch.float32, device=src.device)

@@ -53,6 +53,20 @@ def grad_ok(g, ref):
     return float((err / tol).max()), bool((err <= tol).all())
 
 
+def s2m_ok(got, ref32, ref64):
+    """
+    Parity of the specular->metallic conversion with an sRGB albedo (diffuse.py:129-147).  It divides by
+    (decode(albedo) - 0.04 + 2e-6), which amplifies ONE ulp of the decode by up to 2e-3 relative near 0.04, so no
+    implementation whose pow differs from ATen's by an ulp anywhere can be inside rel 1e-5 on every texel.  The statement
+    is SURVEY.md 8c's: inside rel 1e-5 of the reference, or not further from the reference's own fp64 evaluation than
+    twice the reference is.  Returns (fraction inside plain rel 1e-5, all texels pass).
+    """
+    got, ref32, ref64 = (np.asarray(x, np.float64) for x in (got, ref32, ref64))
+    plain = np.abs(got - ref32) <= 1e-5 * np.abs(ref32) + 1e-6
+    arb = np.abs(got - ref64) <= 2 * np.abs(ref32 - ref64) + 1e-6
+    return float(plain.mean()), bool((plain | arb).all())
+
+
 @pytest.fixture(scope="session")
 def hostsim():
     """The device math headers compiled for the host (tests/hostsim/hostsim.cpp)."""

@@ -259,6 +259,17 @@ def make_conversion_cases():
         assert bm.metallic.shape[0] == 3
         arrs[f"s2m_basecolor_srgb{int(srgb)}"] = bm.albedo.numpy()
         arrs[f"s2m_metallic_srgb{int(srgb)}"] = bm.metallic.numpy()
+        # fp64 arbiter: the division by (diffuse - 0.04) amplifies an ulp of the sRGB decode without bound near 0.04, so
+        # parity there is stated against the reference's own distance from its fp64 evaluation
+        m64 = DiffuseSpecularMaterial()
+        m64.albedo_is_srgb = srgb
+        for k in ("albedo", "normal", "roughness", "specular"):
+            m64._maps[k] = smaps[k].double()
+        bm64 = m64.to_basecolor_metallic_material()
+        ob64, om64 = O.specular_to_metallic(smaps["albedo"].double(), smaps["specular"].double(), srgb)
+        assert bits_equal(ob64, bm64.albedo) and bits_equal(om64, bm64.metallic)
+        arrs[f"s2m_basecolor64_srgb{int(srgb)}"] = bm64.albedo.numpy()
+        arrs[f"s2m_metallic64_srgb{int(srgb)}"] = bm64.metallic.numpy()
     arrs.update({f"in_m_{k}": v.numpy() for k, v in maps.items()})
     arrs.update({f"in_s_{k}": v.numpy() for k, v in smaps.items()})
     np.savez_compressed(os.path.join(HERE, "convert_31x45.npz"), **arrs)
@@ -369,6 +380,143 @@ def make_geomgrad_cases():
     np.savez_compressed(os.path.join(HERE, "geomgrad_shared_params.npz"), **arrs)
 
 
+def make_autograd_cases():
+    """
+    Autograd THROUGH the conversions, blends, normal ingestion and index transforms, from the reference's own torch graph
+    (metallic.py:103-109, diffuse.py:129-147, blending/functional.py:104-145,187-194, materials/base.py:215-242,521-537,
+    605-655), fp32 and fp64; the oracle's restatement must agree bit for bit.  Written to autograd_convert_blend.npz.
+    """
+    gen = torch.Generator().manual_seed(2025)
+    H, W = 23, 38
+    arrs = {}
+
+    def leafs(d, dtype):
+        return {k: v.to(dtype).clone().requires_grad_(True) for k, v in d.items()}
+
+    def put(cls, leaves, **flags):
+        m = cls()
+        for k, v in flags.items():
+            setattr(m, k, v)
+        for k, v in leaves.items():
+            m._maps[k] = v   # (bypasses the FloatTensor gate: fp64 and requires_grad leaves, as for the shading cases)
+        for k in ("normal", "roughness"):
+            m._maps.setdefault(k, None)   # the conversions read both attributes (metallic.py:115-116)
+        return m
+
+    # ---- conversions
+    mm = synth_maps(gen, H, W, "metallic")
+    sm = synth_maps(gen, H, W, "specular")
+    sm["albedo"][:, :3] = 0.04
+    sm["specular"][:, 3:6] = 0.99
+    sm["albedo"][:, 6:8] = 0.0
+    g0, g1 = torch.randn(3, H, W, generator=gen), torch.randn(3, H, W, generator=gen)
+    arrs.update({f"m2s_in_{k}": mm[k].numpy() for k in ("albedo", "metallic")})
+    arrs.update({f"s2m_in_{k}": sm[k].numpy() for k in ("albedo", "specular")})
+    arrs.update(conv_g0=g0.numpy(), conv_g1=g1.numpy())
+    for srgb in (True, False):
+        for dtype, tag in ((torch.float32, "32"), (torch.float64, "64")):
+            lv = leafs({k: mm[k] for k in ("albedo", "metallic")}, dtype)
+            d = put(BasecolorMetallicMaterial, lv, albedo_is_srgb=srgb).to_diffuse_specular_material()
+            ((d.albedo * g0.to(dtype)).sum() + (d.specular * g1.to(dtype)).sum()).backward()
+            ol = leafs({k: mm[k] for k in ("albedo", "metallic")}, dtype)
+            od, os_ = O.metallic_to_specular(ol["albedo"], ol["metallic"], srgb)
+            ((od * g0.to(dtype)).sum() + (os_ * g1.to(dtype)).sum()).backward()
+            for k in lv:
+                assert bits_equal(lv[k].grad, ol[k].grad), ("m2s", k, srgb, tag)
+                arrs[f"m2s_srgb{int(srgb)}_g{tag}_{k}"] = lv[k].grad.numpy()
+            lv = leafs({k: sm[k] for k in ("albedo", "specular")}, dtype)
+            b = put(DiffuseSpecularMaterial, lv, albedo_is_srgb=srgb).to_basecolor_metallic_material()
+            ((b.albedo * g0.to(dtype)).sum() + (b.metallic * g1.to(dtype)).sum()).backward()
+            ol = leafs({k: sm[k] for k in ("albedo", "specular")}, dtype)
+            ob, om = O.specular_to_metallic(ol["albedo"], ol["specular"], srgb)
+            ((ob * g0.to(dtype)).sum() + (om * g1.to(dtype)).sum()).backward()
+            for k in lv:
+                assert bits_equal(lv[k].grad, ol[k].grad), ("s2m", k, srgb, tag)
+                arrs[f"s2m_srgb{int(srgb)}_g{tag}_{k}"] = lv[k].grad.numpy()
+
+    # ---- blends (mask given / height sigmoid), every map a leaf
+    m1 = synth_maps(gen, H, W, "metallic")
+    m2 = synth_maps(gen, H, W, "metallic", normal="raw")
+    m1["height"] = torch.rand(1, H, W, generator=gen)
+    m2["height"] = torch.rand(1, H, W, generator=gen)
+    mask = torch.rand(1, H, W, generator=gen)
+    names = ("albedo", "normal", "roughness", "metallic", "height")
+    gout = {k: torch.randn(m1[k].shape, generator=gen) for k in names}
+    gmask = torch.randn(1, H, W, generator=gen)
+    arrs.update({f"blend_in1_{k}": m1[k].numpy() for k in names})
+    arrs.update({f"blend_in2_{k}": m2[k].numpy() for k in names})
+    arrs["blend_mask"] = mask.numpy()
+    arrs.update({f"blend_gout_{k}": v.numpy() for k, v in gout.items()})
+    arrs["blend_gmask"] = gmask.numpy()
+    for mode in ("mask", "height"):
+        for dtype, tag in ((torch.float32, "32"), (torch.float64, "64")):
+            l1, l2 = leafs(m1, dtype), leafs(m2, dtype)
+            mk = mask.to(dtype).clone().requires_grad_(True)
+            a, b = put(BasecolorMetallicMaterial, l1), put(BasecolorMetallicMaterial, l2)
+            kw = dict(method="mask", mask=mk) if mode == "mask" else dict(method="height", blend_width=0.15)
+            blended, used = ref_blend_materials(a, b, **kw)
+            # (fp64 maps fail the FloatTensor gate of base.py:96-101 and land as plain attributes: getattr finds both)
+            assert float(getattr(blended, "normal").detach().min()) < 0   # the setattr re-ingestion keeps the blended normal as it is
+            loss = sum((getattr(blended, k) * gout[k].to(dtype)).sum() for k in names)
+            if mode == "height":
+                loss = loss + (used * gmask.to(dtype)).sum()
+            loss.backward()
+            o1, o2 = leafs(m1, dtype), leafs(m2, dtype)
+            omk = mask.to(dtype).clone().requires_grad_(True)
+            om = omk if mode == "mask" else O.sigmoid_mask(o1["height"], o2["height"], 0.15)
+            ob = O.blend_maps(o1, o2, om)
+            oloss = sum((ob[k] * gout[k].to(dtype)).sum() for k in names)
+            if mode == "height":
+                oloss = oloss + (om * gmask.to(dtype)).sum()
+            oloss.backward()
+            for k in names:
+                if mode == "height" and k == "height":   # sums over the maps again (through the sigmoid): order, see below
+                    assert torch.allclose(l1[k].grad, o1[k].grad, rtol=1e-5, atol=1e-6) and torch.allclose(l2[k].grad, o2[k].grad, rtol=1e-5, atol=1e-6)
+                else:
+                    assert bits_equal(l1[k].grad, o1[k].grad) and bits_equal(l2[k].grad, o2[k].grad), (mode, k, tag)
+                arrs[f"blend_{mode}_g{tag}_in1_{k}"] = l1[k].grad.numpy()
+                arrs[f"blend_{mode}_g{tag}_in2_{k}"] = l2[k].grad.numpy()
+            if mode == "mask":
+                # the mask gradient is a sum over the maps, accumulated by autograd in graph order: the reference walks a
+                # Python set of names (functional.py:92), the oracle a sorted list - same terms, another order
+                assert torch.allclose(mk.grad, omk.grad, rtol=1e-5, atol=1e-6)
+                arrs[f"blend_mask_g{tag}_mask"] = mk.grad.numpy()
+
+    # ---- normal ingestion: 3-channel RGB-encoded and 2-channel maps (base.py:215-217, :235-242)
+    rgb = torch.rand(3, H, W, generator=gen)
+    two = torch.rand(2, H, W, generator=gen)
+    gn = torch.randn(3, H, W, generator=gen)
+    arrs.update(ingest_in3=rgb.numpy(), ingest_in2=two.numpy(), ingest_gout=gn.numpy())
+    from pypbr.materials import MaterialBase as RefBase
+
+    for dtype, tag in ((torch.float32, "32"), (torch.float64, "64")):
+        for key, src in (("3", rgb), ("2", two)):
+            leaf = src.to(dtype).clone().requires_grad_(True)
+            out = RefBase()._process_normal_map(leaf)
+            (out * gn.to(dtype)).sum().backward()
+            ol = src.to(dtype).clone().requires_grad_(True)
+            (O.process_normal_map(ol) * gn.to(dtype)).sum().backward()
+            assert bits_equal(leaf.grad, ol.grad), ("ingest", key, tag)
+            arrs[f"ingest{key}_g{tag}"] = leaf.grad.numpy()
+
+    # ---- index transforms: flip / roll / tile of a material whose maps are leaves
+    tm = {"albedo": torch.rand(3, 10, 14, generator=gen), "normal": torch.randn(3, 10, 14, generator=gen)}
+    arrs.update({f"index_in_{k}": v.numpy() for k, v in tm.items()})
+    ops = {"flip_h": lambda m: m.flip_horizontal(), "flip_v": lambda m: m.flip_vertical(), "roll": lambda m: m.roll((3, -5)),
+           "tile": lambda m: m.tile(3)}
+    for op, fn in ops.items():
+        lv = leafs(tm, torch.float32)
+        m = fn(put(BasecolorMetallicMaterial, lv))
+        gs = {k: torch.randn(m._maps[k].shape, generator=gen) for k in tm}
+        sum((m._maps[k] * gs[k]).sum() for k in tm).backward()
+        for k in tm:
+            arrs[f"index_{op}_gout_{k}"] = gs[k].numpy()
+            arrs[f"index_{op}_g32_{k}"] = lv[k].grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "autograd_convert_blend.npz"), **arrs)
+    print("autograd_convert_blend: ok")
+
+
+
 def make_height_from_normal_fixture():
     """compute_height_from_normal / compute_normal_from_height of the reference itself (utils/functions.py:123-323)."""
     from pypbr.utils import NormalConvention as RefConv
@@ -394,6 +542,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "height":
         make_height_from_normal_fixture()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "convert":
+        make_conversion_cases()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "autograd":   # only this fixture (the others are unchanged)
+        make_autograd_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "geomgrad":   # only this fixture (the others are unchanged)
         make_geomgrad_cases()
         sys.exit(0)
@@ -403,4 +557,5 @@ if __name__ == "__main__":
     make_blend_cases()
     make_config1_fixture()
     make_geomgrad_cases()
+    make_autograd_cases()
     make_height_from_normal_fixture()

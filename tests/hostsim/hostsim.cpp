@@ -268,7 +268,8 @@ void hs_convert_m2s(int64_t n_texels, int albedo_is_srgb, const float* albedo, c
   // single material (3, n_texels) planar
   for (int64_t i = 0; i < n_texels; ++i) {
     float a[3] = {albedo[i], albedo[n_texels + i], albedo[2 * n_texels + i]}, dd[3], ss[3];
-    convert_m2s(a, met[i], albedo_is_srgb != 0, dd, ss);
+    const float m3[3] = {met[i], met[i], met[i]};
+    convert_m2s(a, m3, albedo_is_srgb != 0, dd, ss);
     for (int c = 0; c < 3; ++c) {
       diffuse[c * n_texels + i] = dd[c];
       specular[c * n_texels + i] = ss[c];
@@ -323,6 +324,63 @@ void hs_ingest_normal(int64_t n_texels, int channels, const float* in, float* ou
       ingest_normal2(v, o);
     }
     for (int c = 0; c < 3; ++c) out[c * n_texels + i] = o[c];
+  }
+}
+
+// ---- adjoints of the streaming kernels (pbr_grad_kernels.cuh runs these per texel)
+void hs_convert_m2s_bwd(int64_t n, int albedo_is_srgb, int met_channels, const float* albedo, const float* met, const float* g0,
+                        const float* g1, float* d_albedo, float* d_met) {
+  for (int64_t i = 0; i < n; ++i) {
+    const float a[3] = {albedo[i], albedo[n + i], albedo[2 * n + i]};
+    const float m3[3] = {met[i], met_channels == 3 ? met[n + i] : met[i], met_channels == 3 ? met[2 * n + i] : met[i]};
+    const float gd[3] = {g0[i], g0[n + i], g0[2 * n + i]}, gs[3] = {g1[i], g1[n + i], g1[2 * n + i]};
+    float da[3], dm[3];
+    convert_m2s_bwd(a, m3, albedo_is_srgb != 0, gd, gs, da, dm);
+    for (int c = 0; c < 3; ++c) d_albedo[c * n + i] = da[c];
+    if (met_channels == 3) for (int c = 0; c < 3; ++c) d_met[c * n + i] = dm[c];
+    else d_met[i] = (dm[0] + dm[1]) + dm[2];
+  }
+}
+
+void hs_convert_s2m_bwd(int64_t n, int albedo_is_srgb, const float* diffuse, const float* specular, const float* g_b, const float* g_m,
+                        float* d_albedo, float* d_spec) {
+  for (int64_t i = 0; i < n; ++i) convert_s2m_bwd(diffuse[i], specular[i], albedo_is_srgb != 0, g_b[i], g_m[i], &d_albedo[i], &d_spec[i]);
+}
+
+// one map of a blend: d_a, d_b, and dmask += this map's contribution
+void hs_blend_bwd(int64_t n, int channels, int is_normal, const float* mask, const float* a, const float* b, const float* g,
+                  float* d_a, float* d_b, float* dmask) {
+  for (int64_t i = 0; i < n; ++i) {
+    if (is_normal) {
+      const float aa[3] = {a[i], a[n + i], a[2 * n + i]}, bb[3] = {b[i], b[n + i], b[2 * n + i]}, gg[3] = {g[i], g[n + i], g[2 * n + i]};
+      float da[3], db[3];
+      dmask[i] += blend_normal_bwd(mask[i], aa, bb, gg, da, db);
+      for (int c = 0; c < 3; ++c) { d_a[c * n + i] = da[c]; d_b[c * n + i] = db[c]; }
+    } else {
+      for (int c = 0; c < channels; ++c) {
+        const float go = g[c * n + i];
+        dmask[i] += go * (a[c * n + i] - b[c * n + i]);
+        d_a[c * n + i] = mask[i] * go;
+        d_b[c * n + i] = (1.0f - mask[i]) * go;
+      }
+    }
+  }
+}
+
+void hs_ingest_normal_bwd(int64_t n, int channels, const float* in, const float* g, float* d_in) {
+  for (int64_t i = 0; i < n; ++i) {
+    const float gg[3] = {g[i], g[n + i], g[2 * n + i]};
+    if (channels == 3) {
+      const float v[3] = {in[i], in[n + i], in[2 * n + i]};
+      float d[3];
+      ingest_normal3_bwd(v, gg, d);
+      for (int c = 0; c < 3; ++c) d_in[c * n + i] = d[c];
+    } else {
+      const float v[2] = {in[i], in[n + i]};
+      float d[2];
+      ingest_normal2_bwd(v, gg, d);
+      d_in[i] = d[0]; d_in[n + i] = d[1];
+    }
   }
 }
 

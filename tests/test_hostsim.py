@@ -4,12 +4,13 @@ golden vectors: proves, without a GPU, that the expressions the kernels execute 
 reference within the stated tolerances (only the MUFU pow / rsqrt / rcp seeds differ on the device).
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
 import torch
 
-from conftest import case_inputs, fwd_ok, golden_ct_cases, grad_ok, load_golden
+from conftest import GOLDEN, s2m_ok, case_inputs, fwd_ok, golden_ct_cases, grad_ok, load_golden
 
 F = ctypes.POINTER(ctypes.c_float)
 D = ctypes.POINTER(ctypes.c_double)
@@ -150,11 +151,10 @@ def test_conversions_match_golden(hostsim):
         hostsim.hs_convert_s2m(ctypes.c_int64(3 * n), srgb, fp(a), fp(sp), fp(b), fp(mm))
         rb, rm = z[f"s2m_basecolor_srgb{srgb}"], z[f"s2m_metallic_srgb{srgb}"]
         if srgb:
-            # the metallic heuristic divides by (d - 0.04 + 2e-6): a 1-ulp change of the decoded albedo is
-            # amplified without bound near d = 0.04, so compare where the reference itself is well conditioned
-            dlin = O_srgb(a)
-            well = np.abs(dlin - 0.04) > 1e-3
-            assert np.allclose(b[well], rb[well], rtol=2e-4, atol=1e-6) and np.allclose(mm[well], rm[well], rtol=2e-4, atol=1e-6)
+            # every texel (conftest.s2m_ok): rel 1e-5, or within twice the reference's own distance from its fp64 run
+            for got, key in ((b, "basecolor"), (mm, "metallic")):
+                frac, ok = s2m_ok(got, z[f"s2m_{key}_srgb1"], z[f"s2m_{key}64_srgb1"])
+                assert ok and frac > 0.995, (key, frac)
         else:
             assert np.array_equal(b, rb) and np.array_equal(mm, rm)
 
@@ -330,3 +330,42 @@ def test_saturated_accumulate_backward_one_and_two_pass(hostsim, flags):
     for k, g in (("albedo", da), ("normal", dn), ("roughness", dr), ("metallic", dm)):
         ratio, ok = grad_ok(g, leaves[k].grad.numpy())
         assert ok, f"d_{k}: {ratio}"
+
+
+def test_adjoints_of_conversions_blends_and_ingestion_match_reference_autograd(hostsim):
+    """The per-texel adjoint code of pbr_grad_kernels.cuh (convert / blend / normal-ingest backward), compiled for the host,
+    against the REFERENCE's own autograd results (tests/golden/autograd_convert_blend.npz, written by make_golden.py)."""
+    z = np.load(os.path.join(GOLDEN, "autograd_convert_blend.npz"))
+    c = lambda k: np.ascontiguousarray(z[k])
+    H, W = z["conv_g0"].shape[-2:]
+    n = H * W
+    g0, g1 = c("conv_g0"), c("conv_g1")
+    for srgb in (1, 0):
+        a, m = c("m2s_in_albedo"), c("m2s_in_metallic")
+        da, dm = np.zeros_like(a), np.zeros_like(m)
+        hostsim.hs_convert_m2s_bwd(ctypes.c_int64(n), srgb, 1, fp(a), fp(m), fp(g0), fp(g1), fp(da), fp(dm))
+        assert grad_ok(da, z[f"m2s_srgb{srgb}_g32_albedo"])[1] and grad_ok(dm, z[f"m2s_srgb{srgb}_g32_metallic"])[1]
+        a, sp = c("s2m_in_albedo"), c("s2m_in_specular")
+        da, ds = np.zeros_like(a), np.zeros_like(sp)
+        hostsim.hs_convert_s2m_bwd(ctypes.c_int64(3 * n), srgb, fp(a), fp(sp), fp(g0), fp(g1), fp(da), fp(ds))
+        for got, key in ((da, "albedo"), (ds, "specular")):
+            # the same ill-conditioned division as the forward: judged against the fp64 run where fp32 autograd itself is off
+            r32, r64 = z[f"s2m_srgb{srgb}_g32_{key}"], z[f"s2m_srgb{srgb}_g64_{key}"]
+            tol = 1e-4 * np.abs(r32) + 1e-4 * np.abs(r32).mean()
+            ok = (np.abs(got - r32) <= tol) | (np.abs(got - r64) <= 2 * np.abs(r32.astype(np.float64) - r64) + tol)
+            assert ok.mean() > 0.999, (key, srgb, ok.mean())
+    names = ("albedo", "normal", "roughness", "metallic", "height")
+    mask = c("blend_mask")
+    dmask = np.zeros_like(mask)
+    for k in names:
+        a, b, g = c(f"blend_in1_{k}"), c(f"blend_in2_{k}"), c(f"blend_gout_{k}")
+        da, db = np.zeros_like(a), np.zeros_like(b)
+        hostsim.hs_blend_bwd(ctypes.c_int64(n), a.shape[0], int(k == "normal"), fp(mask), fp(a), fp(b), fp(g), fp(da), fp(db), fp(dmask))
+        assert grad_ok(da, z[f"blend_mask_g32_in1_{k}"])[1] and grad_ok(db, z[f"blend_mask_g32_in2_{k}"])[1], k
+    assert grad_ok(dmask, z["blend_mask_g32_mask"])[1]
+    gn = c("ingest_gout")
+    for ch in (3, 2):
+        src = c(f"ingest_in{ch}")
+        d = np.zeros_like(src)
+        hostsim.hs_ingest_normal_bwd(ctypes.c_int64(n), ch, fp(src), fp(gn), fp(d))
+        assert grad_ok(d, z[f"ingest{ch}_g32"])[1], ch
