@@ -163,6 +163,7 @@ struct CtKParams {
   int mats_per_cta;      // materials a thread walks over (blockIdx.z selects the chunk)
   CtFlags flags;
   int vec_ok;
+  int vec_fast;          // host: the kVec = true flavour of the generic kernels applies (see locate_ct)
   int is_loss;           // backward: grad_out is derived from (render - target)
   int force_generic;     // PbrCtDesc.force_generic
   PbrPlane albedo, normal, roughness, metspec, out;
@@ -211,34 +212,56 @@ __device__ __forceinline__ void stage_params(const CtKParams& p, CtStage& S) {
   __syncthreads();
 }
 
-// Generic Cook-Torrance kernels: the vector path is taken by the whole grid or not at all (W a multiple of the
-// texels per thread => no thread has a ragged segment), so the choice depends on kernel parameters only and compiles
-// to a uniform branch instead of predicated copies of both paths inside the light loop.
+// Generic Cook-Torrance kernels come in two flavours (template parameter kVec):
+//   kVec = true : the fast flavour.  The host has checked that every plane is 8-byte aligned with even strides, that W is a
+//                 multiple of the texels per thread (no thread has a ragged segment) and that every in-plane offset fits
+//                 32 bits.  Loads / stores / cp.async are 64-bit with no fallback code in the instruction stream, and an
+//                 address is a uniform 64-bit base (plane pointer + batch and channel strides: the same for the whole
+//                 CTA) plus ONE 32-bit per-thread offset - the predicated-off scalar copies and the 64-bit per-thread
+//                 address arithmetic were a fifth of the fused fit kernel's instructions (profiles/r1_ncu_summary.md).
+//   kVec = false: any alignment, ragged widths, planes beyond 2^31 elements: element accesses, 64-bit offsets; only the
+//                 uncached light modes are instantiated for it (light_mode()).
+template <bool kVec>
 __device__ __forceinline__ Where locate_ct(const CtKParams& p) {
   Where w = locate_n<kCtTexels>(p.H, p.W, p.vec_ok != 0);
-  w.vec = p.vec_ok != 0 && (p.W % kCtTexels) == 0;
+  if (kVec) {
+    w.vec = true;
+    w.valid = kCtTexels;
+  } else {
+    w.vec = p.vec_ok != 0 && (p.W % kCtTexels) == 0;
+  }
   return w;
 }
 
-template <int WF>
+template <bool kVec> struct OffT { typedef int64_t type; };
+template <> struct OffT<true> { typedef int type; };
+// element (b, c, w.row, w.col0 + dcol) of a plane: uniform base + per-thread offset
+template <bool kVec>
+__device__ __forceinline__ float* at(const PbrPlane& pl, int b, int c, const Where& w, int dcol = 0) {
+  typedef typename OffT<kVec>::type T;
+  float* base = pl.ptr + ((int64_t)b * pl.sb + (int64_t)c * pl.sc);
+  return base + ((T)w.row * (T)pl.sh + (T)(w.col0 + dcol));
+}
+
+template <int WF, bool kVec>
 __device__ __forceinline__ void load_material(const CtKParams& p, const Where& w, int b, float (&araw)[3][kCtTexels],
                                               float (&nraw)[3][kCtTexels], float (&rough)[kCtTexels],
                                               float (&mraw)[3][kCtTexels]) {
 #pragma unroll
-  for (int c = 0; c < 3; ++c) load_seg<kCtTexels>(p.albedo.ptr + plane_off(p.albedo, b, c, w.row, w.col0), w.vec, w.valid, araw[c]);
+  for (int c = 0; c < 3; ++c) load_seg<kCtTexels>(at<kVec>(p.albedo, b, c, w), w.vec, w.valid, araw[c]);
   if (p.normal.ptr) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) load_seg<kCtTexels>(p.normal.ptr + plane_off(p.normal, b, c, w.row, w.col0), w.vec, w.valid, nraw[c]);
+    for (int c = 0; c < 3; ++c) load_seg<kCtTexels>(at<kVec>(p.normal, b, c, w), w.vec, w.valid, nraw[c]);
   } else {
 #pragma unroll
     for (int i = 0; i < kCtTexels; ++i) { nraw[0][i] = 0.0f; nraw[1][i] = 0.0f; nraw[2][i] = 1.0f; }
   }
-  load_seg<kCtTexels>(p.roughness.ptr + plane_off(p.roughness, b, 0, w.row, w.col0), w.vec, w.valid, rough);
+  load_seg<kCtTexels>(at<kVec>(p.roughness, b, 0, w), w.vec, w.valid, rough);
   constexpr int mc = WF == 0 ? 1 : 3;  // WF: 0 metallic (1 ch), 1 specular, 2 metallic (3 ch)
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     if (c < mc) {
-      load_seg<kCtTexels>(p.metspec.ptr + plane_off(p.metspec, b, c, w.row, w.col0), w.vec, w.valid, mraw[c]);
+      load_seg<kCtTexels>(at<kVec>(p.metspec, b, c, w), w.vec, w.valid, mraw[c]);
     } else {
 #pragma unroll
       for (int i = 0; i < kCtTexels; ++i) mraw[c][i] = 0.0f;
@@ -262,18 +285,18 @@ constexpr bool kFwdRegPrefetch = PBR_FWD_REG_PREFETCH != 0;
 #endif
 __device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-template <int WF>
+template <int WF, bool kVec>
 __device__ __forceinline__ void prefetch_material(const CtKParams& p, const Where& w, int b) {
   if (!PBR_PREFETCH_NEXT || ((threadIdx.x * kCtTexels) & 31) != 0) return;   // first thread of every 128-byte line
 #pragma unroll
-  for (int c = 0; c < 3; ++c) prefetch_l2(p.albedo.ptr + plane_off(p.albedo, b, c, w.row, w.col0));
+  for (int c = 0; c < 3; ++c) prefetch_l2(at<kVec>(p.albedo, b, c, w));
   if (p.normal.ptr) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) prefetch_l2(p.normal.ptr + plane_off(p.normal, b, c, w.row, w.col0));
+    for (int c = 0; c < 3; ++c) prefetch_l2(at<kVec>(p.normal, b, c, w));
   }
-  prefetch_l2(p.roughness.ptr + plane_off(p.roughness, b, 0, w.row, w.col0));
+  prefetch_l2(at<kVec>(p.roughness, b, 0, w));
 #pragma unroll
-  for (int c = 0; c < (WF == 0 ? 1 : 3); ++c) prefetch_l2(p.metspec.ptr + plane_off(p.metspec, b, c, w.row, w.col0));
+  for (int c = 0; c < (WF == 0 ? 1 : 3); ++c) prefetch_l2(at<kVec>(p.metspec, b, c, w));
 }
 
 // texels [kLanes*s0, kLanes*(s0+G)) of a thread's row segment as G lane-values
@@ -333,12 +356,12 @@ __device__ __forceinline__ void grid_coords(const CtStage& S, const Where& w, in
   }
 }
 
-template <int WF, int kLight>
+template <int WF, int kLight, bool kVec = true>
 __global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kernel(const __grid_constant__ CtKParams p) {
   constexpr int G = PBR_FWD_GROUP;
   __shared__ CtStage S;
   stage_params(p, S);
-  const Where w = locate_ct(p);
+  const Where w = locate_ct<kVec>(p);
   if (!w.active) return;
 
   V x[kSlots];
@@ -353,7 +376,7 @@ __global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kerne
   // are loaded into a second register set while the current one is shaded (the backward, at 235 registers, prefetches
   // into L2 instead).
   float nx_a[3][kCtTexels], nx_n[3][kCtTexels], nx_r[kCtTexels], nx_m[3][kCtTexels];
-  if (kFwdRegPrefetch) load_material<WF>(p, w, b0, nx_a, nx_n, nx_r, nx_m);
+  if (kFwdRegPrefetch) load_material<WF, kVec>(p, w, b0, nx_a, nx_n, nx_r, nx_m);
   for (int b = b0; b < b1; ++b) {
     float araw[3][kCtTexels], nraw[3][kCtTexels], rough[kCtTexels], mraw[3][kCtTexels];
     if (kFwdRegPrefetch) {
@@ -363,10 +386,10 @@ __global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kerne
         for (int c = 0; c < 3; ++c) { araw[c][i] = nx_a[c][i]; nraw[c][i] = nx_n[c][i]; mraw[c][i] = nx_m[c][i]; }
         rough[i] = nx_r[i];
       }
-      if (b + 1 < b1) load_material<WF>(p, w, b + 1, nx_a, nx_n, nx_r, nx_m);
+      if (b + 1 < b1) load_material<WF, kVec>(p, w, b + 1, nx_a, nx_n, nx_r, nx_m);
     } else {
-      load_material<WF>(p, w, b, araw, nraw, rough, mraw);
-      if (b + 1 < b1) prefetch_material<WF>(p, w, b + 1);
+      load_material<WF, kVec>(p, w, b, araw, nraw, rough, mraw);
+      if (b + 1 < b1) prefetch_material<WF, kVec>(p, w, b + 1);
     }
     float outv[3][kCtTexels];
 #pragma unroll
@@ -384,7 +407,7 @@ __global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kerne
             float tv[kLanes * G];
             unpair_to<G>(v[c], 0, tv);
             int vs = w.valid - kLanes * s;
-            store_seg<kLanes * G>(p.out.ptr + plane_off(p.out, b, c, w.row, w.col0 + kLanes * s) + (int64_t)l * p.out_sl,
+            store_seg<kLanes * G>(at<kVec>(p.out, b, c, w, kLanes * s) + (int64_t)l * p.out_sl,
                                   w.vec, vs < 0 ? 0 : vs, tv);
           }
         } else {
@@ -399,7 +422,7 @@ __global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kerne
     if (!p.flags.per_light) {
 #pragma unroll
       for (int c = 0; c < 3; ++c)
-        store_seg<kCtTexels>(p.out.ptr + plane_off(p.out, b, c, w.row, w.col0), w.vec, w.valid, outv[c]);
+        store_seg<kCtTexels>(at<kVec>(p.out, b, c, w), w.vec, w.valid, outv[c]);
     }
   }
 }
@@ -482,7 +505,7 @@ struct CtaGeomSink {
 
 // kGeom: also d/d(light position | direction) and d/d(view direction) (PbrCtGrads.d_lights / d_view), which the
 // reference delivers through plain autograd (cooktorrance.py:95,125-140).  Uncached per-texel light modes only.
-template <int WF, int kLight, bool kGeom = false>
+template <int WF, int kLight, bool kGeom = false, bool kVec = true>
 __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) ct_backward_kernel(const __grid_constant__ CtKParams p) {
   constexpr int G = PBR_BWD_GROUP;
   __shared__ CtStage S;
@@ -500,7 +523,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
     for (int i = tid; i < (p.flags.L + 1) * 3; i += kCtThreads) s_geo[i] = 0.0f;
   }
   stage_params(p, S);  // ends with __syncthreads()
-  const Where w = locate_ct(p);
+  const Where w = locate_ct<kVec>(p);
   const float live = w.active ? 1.0f : 0.0f;
   if (!w.active && !int_grad && !is_loss && !kGeom) return;  // nothing to reduce: edge threads may leave
 
@@ -532,9 +555,9 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
         rough[i] = nx_r[i];
       }
     } else {
-      load_material<WF>(p, w, b, araw, nraw, rough, mraw);
+      load_material<WF, kVec>(p, w, b, araw, nraw, rough, mraw);
     }
-    if (b + 1 < b1) prefetch_material<WF>(p, w, b + 1);
+    if (b + 1 < b1) prefetch_material<WF, kVec>(p, w, b + 1);
     if (p.adam_on) {
       // Fused fit step: what the Adam epilogue of THIS material needs (parameters and both moments of every channel)
       // starts travelling now, as per-thread cp.async copies into shared memory, and lands while the light loop runs.
@@ -543,12 +566,12 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       // so the ring's first wait also covers it.
       int ch = 0;
       auto send = [&](const PbrPlane& P, int q, int c) {
-        const float* src[3] = {P.ptr + plane_off(P, b, c, w.row, w.col0), p.adam_m[q].ptr + plane_off(p.adam_m[q], b, c, w.row, w.col0),
-                               p.adam_v[q].ptr + plane_off(p.adam_v[q], b, c, w.row, w.col0)};
+        const float* src[3] = {at<kVec>(P, b, c, w), at<kVec>(p.adam_m[q], b, c, w),
+                               at<kVec>(p.adam_v[q], b, c, w)};
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           float* dst = s_adam + ((3 * ch + j) * kCtThreads) * kCtTexels;
-          if (kCtTexels == 2 && w.vec) {
+          if (kCtTexels == 2 && (kVec || w.vec)) {
             cp_async8(dst, src[j]);
           } else {
 #pragma unroll kColdUnroll   // cold path, branched over
@@ -587,9 +610,9 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       constexpr int NT = kLanes * G;
       float* ring = s_ring + tid * NT;   // [slot][channel][thread][NT]
       const int nl_src = p.flags.per_light ? p.flags.L : 1;
-      const float* const gbase = p.gsrc.ptr + plane_off(p.gsrc, b, 0, w.row, w.col0 + kLanes * s);   // once per material
+      const float* const gbase = at<kVec>(p.gsrc, b, 0, w, kLanes * s);   // once per material
       const bool have_fout = p.fout.ptr != nullptr;   // accumulate mode only (nl_src == 1): slot 1 carries the saved forward output
-      const float* const fbase = have_fout ? p.fout.ptr + plane_off(p.fout, b, 0, w.row, w.col0 + kLanes * s) : nullptr;
+      const float* const fbase = have_fout ? at<kVec>(p.fout, b, 0, w, kLanes * s) : nullptr;
       auto issue = [&](int l) {
         const bool saved = have_fout && l == 1;
         if (l < nl_src || saved) {
@@ -599,7 +622,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
           for (int c = 0; c < 3; ++c) {
             const float* src = gl + (int64_t)c * csc;
             float* dst = ring + ((l % kRing) * 3 + c) * (kCtThreads * NT);
-            if (NT == 2 && w.vec) {
+            if (NT == 2 && (kVec || w.vec)) {
               cp_async8(dst, src);
             } else {
 #pragma unroll kColdUnroll   // cold path (ragged or unaligned rows): a real loop is branched over instead of predicated
@@ -611,7 +634,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       };
       auto fetch = [&](int l) {
         if (l < 0) {   // after the light loop
-          if (late_prefetch && s + G >= kSlots && b + 1 < b1) load_material<WF>(p, w, b + 1, nx_a, nx_n, nx_r, nx_m);
+          if (late_prefetch && s + G >= kSlots && b + 1 < b1) load_material<WF, kVec>(p, w, b + 1, nx_a, nx_n, nx_r, nx_m);
           return;
         }
         if (l == 0) {
@@ -631,7 +654,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       };
       auto gout = [&](int l, const V(&outv)[3][G], V(&g)[3][G]) {
         take(l);
-        if (kPackedLoss && w.vec) {   // every lane is a live texel (uniform over the grid): packed arithmetic, no masks
+        if (kPackedLoss && (kVec || w.vec)) {   // every lane is a live texel (uniform over the grid): packed arithmetic, no masks
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             V t[G];
@@ -710,15 +733,15 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
 #pragma unroll
         for (int i = 0; i < kSlots; ++i) pp[i] = adam_update_fast(pp[i], gp[i], mp[i], vp[i], p.adam, inv_b2);
         unpair_to<kSlots>(pp, 0, pn); unpair_to<kSlots>(mp, 0, m); unpair_to<kSlots>(vp, 0, v);
-        store_seg<kCtTexels>(p.adam_m[q].ptr + plane_off(p.adam_m[q], b, c, w.row, w.col0), w.vec, w.valid, m);
-        store_seg<kCtTexels>(p.adam_v[q].ptr + plane_off(p.adam_v[q], b, c, w.row, w.col0), w.vec, w.valid, v);
+        store_seg<kCtTexels>(at<kVec>(p.adam_m[q], b, c, w), w.vec, w.valid, m);
+        store_seg<kCtTexels>(at<kVec>(p.adam_v[q], b, c, w), w.vec, w.valid, v);
       };
       auto put = [&](const PbrPlane& P, int c, float(&pn)[kCtTexels], bool clamp) {
         if (clamp) {
 #pragma unroll
           for (int i = 0; i < kCtTexels; ++i) pn[i] = fminf(fmaxf(pn[i], 0.0f), 1.0f);
         }
-        store_seg<kCtTexels>(const_cast<float*>(P.ptr) + plane_off(P, b, c, w.row, w.col0), w.vec, w.valid, pn);
+        store_seg<kCtTexels>(at<kVec>(P, b, c, w), w.vec, w.valid, pn);
       };
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -756,17 +779,17 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
     } else if (w.active) {
       if (p.d_albedo.ptr) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) store_seg<kCtTexels>(p.d_albedo.ptr + plane_off(p.d_albedo, b, c, w.row, w.col0), w.vec, w.valid, d_albedo[c]);
+        for (int c = 0; c < 3; ++c) store_seg<kCtTexels>(at<kVec>(p.d_albedo, b, c, w), w.vec, w.valid, d_albedo[c]);
       }
       if (p.normal.ptr && p.d_normal.ptr) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) store_seg<kCtTexels>(p.d_normal.ptr + plane_off(p.d_normal, b, c, w.row, w.col0), w.vec, w.valid, d_normal[c]);
+        for (int c = 0; c < 3; ++c) store_seg<kCtTexels>(at<kVec>(p.d_normal, b, c, w), w.vec, w.valid, d_normal[c]);
       }
-      if (p.d_roughness.ptr) store_seg<kCtTexels>(p.d_roughness.ptr + plane_off(p.d_roughness, b, 0, w.row, w.col0), w.vec, w.valid, d_rough);
+      if (p.d_roughness.ptr) store_seg<kCtTexels>(at<kVec>(p.d_roughness, b, 0, w), w.vec, w.valid, d_rough);
       if (p.d_metspec.ptr) {
         constexpr int mc = WF == 0 ? 1 : 3;
 #pragma unroll
-        for (int c = 0; c < mc; ++c) store_seg<kCtTexels>(p.d_metspec.ptr + plane_off(p.d_metspec, b, c, w.row, w.col0), w.vec, w.valid, d_met[c]);
+        for (int c = 0; c < mc; ++c) store_seg<kCtTexels>(at<kVec>(p.d_metspec, b, c, w), w.vec, w.valid, d_met[c]);
       }
     }
   }
@@ -1109,6 +1132,10 @@ constexpr int kHoistMats = PBR_HOIST_MATS;
 #define PBR_GC_ALL_MAX_LIGHTS 4   // up to here all 8 geometry fields are cached and the backward keeps 3 CTAs per SM
 #endif
 static size_t geom_cache_bytes(int L, int light_mode) { return (size_t)L * geom_fields(light_mode) * kSlots * kCtThreads * sizeof(V); }
+static bool vec_fast_disabled() {   // A/B and test switch: run the element-access flavour on shapes the fast one would take
+  static const bool off = [] { const char* e = getenv("PBR_DISABLE_VEC_FAST"); return e && e[0] && e[0] != '0'; }();
+  return off;
+}
 static bool geom_cache_disabled() {
   static const bool off = [] { const char* e = getenv("PBR_DISABLE_GEOM_CACHE"); return e && e[0] && e[0] != '0'; }();
   return off;
@@ -1117,6 +1144,7 @@ static bool geom_cache_disabled() {
 static int light_mode(const CtKParams& k) {
   if (!k.flags.point) return kLightDirectional;
   if (k.d_lights || k.d_view) return kLightPoint;   // geometry gradients need the per-texel intermediates
+  if (!k.vec_fast) return kLightPoint;              // the element-access flavour only exists for the uncached light modes
   if (k.flags.L == 1) return kLightPointHoisted;
   if (k.B >= 2 && !geom_cache_disabled()) {
     if (k.flags.L <= PBR_GC_ALL_MAX_LIGHTS) return kLightPointCachedAll;
@@ -1154,7 +1182,13 @@ static int kernel_workflow(const PbrCtDesc* d) {
 
 template <int WF>
 static void launch_fwd(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t st) {
-  switch (light_mode(k)) {
+  const int lm = light_mode(k);
+  if (!k.vec_fast) {   // any alignment / ragged width: element accesses, uncached light modes
+    if (lm == kLightDirectional) ct_forward_kernel<WF, kLightDirectional, false><<<grid, block, 0, st>>>(k);
+    else ct_forward_kernel<WF, kLightPoint, false><<<grid, block, 0, st>>>(k);
+    return;
+  }
+  switch (lm) {
     case kLightDirectional: ct_forward_kernel<WF, kLightDirectional><<<grid, block, 0, st>>>(k); break;
     case kLightPoint: ct_forward_kernel<WF, kLightPoint><<<grid, block, 0, st>>>(k); break;
     case kLightPointCached: launch_dyn<ct_forward_kernel<WF, kLightPointCached>>(k, grid, block, geom_cache_bytes(k.flags.L, kLightPointCached), st); break;
@@ -1169,13 +1203,23 @@ constexpr size_t kAdamSmemBytes = (size_t)30 * kCtThreads * kCtTexels * sizeof(f
 template <int WF>
 static void launch_bwd(const CtKParams& k_in, dim3 grid, dim3 block, cudaStream_t st) {
   CtKParams k = k_in;
-  const int lm = (k.d_lights || k.d_view) ? (k.flags.point ? kLightPoint : kLightDirectional) : light_mode(k);
+  const int lm = light_mode(k);
   const size_t cache = is_cached(lm) ? geom_cache_bytes(k.flags.L, lm) : 0;
   k.adam_smem_off = (int)cache;
   const size_t smem = cache + (k.adam_on ? kAdamSmemBytes : 0);
   if (k.d_lights || k.d_view) {   // geometry gradients: the uncached per-texel light modes
-    if (k.flags.point) launch_dyn<ct_backward_kernel<WF, kLightPoint, true>>(k, grid, block, smem, st);
-    else launch_dyn<ct_backward_kernel<WF, kLightDirectional, true>>(k, grid, block, smem, st);
+    if (k.vec_fast) {
+      if (k.flags.point) launch_dyn<ct_backward_kernel<WF, kLightPoint, true>>(k, grid, block, smem, st);
+      else launch_dyn<ct_backward_kernel<WF, kLightDirectional, true>>(k, grid, block, smem, st);
+    } else {
+      if (k.flags.point) launch_dyn<ct_backward_kernel<WF, kLightPoint, true, false>>(k, grid, block, smem, st);
+      else launch_dyn<ct_backward_kernel<WF, kLightDirectional, true, false>>(k, grid, block, smem, st);
+    }
+    return;
+  }
+  if (!k.vec_fast) {
+    if (lm == kLightDirectional) launch_dyn<ct_backward_kernel<WF, kLightDirectional, false, false>>(k, grid, block, smem, st);
+    else launch_dyn<ct_backward_kernel<WF, kLightPoint, false, false>>(k, grid, block, smem, st);
     return;
   }
   switch (lm) {
@@ -1293,9 +1337,20 @@ void launch_wf2(CtKParams& k, dim3 grid, dim3 block, bool stream, bool backward,
 
 #if PBR_MAIN_PART
 // shared tail of the three Cook-Torrance entry points
+// every in-plane offset (row * sh + col) of a plane fits 32 bits
+static bool planes_fit_i32(const CtKParams& k) {
+  const PbrPlane* all[] = {&k.albedo, &k.normal, &k.roughness, &k.metspec, &k.out, &k.gsrc, &k.fout, &k.d_albedo, &k.d_normal,
+                           &k.d_roughness, &k.d_metspec, &k.adam_m[0], &k.adam_m[1], &k.adam_m[2], &k.adam_m[3],
+                           &k.adam_v[0], &k.adam_v[1], &k.adam_v[2], &k.adam_v[3]};
+  for (const PbrPlane* pl : all)
+    if (pl->ptr && (pl->sh < 0 || (int64_t)(k.H - 1) * pl->sh + k.W >= (int64_t)INT32_MAX)) return false;
+  return true;
+}
+
 static int ct_dispatch(CtKParams& k, int wf, bool backward, cudaStream_t st) {
   dim3 grid, block;
   int mats = 1;
+  k.vec_fast = k.vec_ok && (k.W % kCtTexels) == 0 && planes_fit_i32(k) && !vec_fast_disabled();
   bool stream = stream_shape(k, grid, block, mats, backward ? kPerWarpBwd : kPerWarpFwd);
   if (stream) {
     if (backward) stream = fits_i32(k.d_albedo, k.H, k.W) && fits_i32(k.d_normal, k.H, k.W) && fits_i32(k.d_roughness, k.H, k.W) && fits_i32(k.d_metspec, k.H, k.W);

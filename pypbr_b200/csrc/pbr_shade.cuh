@@ -158,14 +158,23 @@ PBR_HD void light_geom(const CtStage& S, int l, const V (&x)[N], float y, const 
   }
 }
 
-PBR_HD bool any_ge(float v, float t) { return v >= t; }
-PBR_HD bool any_ge(f2 v, float t) { return v.x >= t || v.y >= t; }
+// Saved forward outputs from which the gate / slope of encode(clamp(sum)) cannot be read off reliably:
+//   out >= top : a sum of exactly 1, above 1, or within an ulp or two below 1 all encode to `top` (torch.clamp's gate is
+//                inclusive at 1);
+//   out within 5e-7 of the knee's image (sRGB only): the two branches of linear_to_srgb do not meet exactly at 0.0031308 -
+//                the power branch starts 7e-8 BELOW 12.92 * knee - so a sum just above the knee encodes to a value the
+//                linear branch also produces, and their slopes differ by 1.8 % (seen once in 12.6 M texels at the C3 shape).
+// Those texels recompute the sum (kBoundaryRecompute); everything else reads the slope off the output.
+constexpr float kKneeImage = 12.92f * kSrgbEncKnee;   // 0.040449936
+PBR_HD bool at_boundary(float v, float top, bool srgb) { return v >= top || (srgb && fabsf(v - kKneeImage) < 5e-7f); }
+PBR_HD bool at_boundary(f2 v, float top, bool srgb) { return at_boundary(v.x, top, srgb) || at_boundary(v.y, top, srgb); }
 
+// c is a colour the caller has just clamped to [0, 1]
 template <class V>
-PBR_HD V encode_out(V c, bool return_srgb) { return return_srgb ? srgb_encode<false>(c, (V*)nullptr) : c; }
+PBR_HD V encode_out(V c, bool return_srgb) { return return_srgb ? srgb_encode01<false>(c, (V*)nullptr) : c; }
 template <class V>
 PBR_HD V encode_out_d(V c, bool return_srgb, V* d) {
-  if (return_srgb) return srgb_encode<true>(c, d);
+  if (return_srgb) return srgb_encode01<true>(c, d);
   *d = splat<V>(1.0f);
   return c;
 }
@@ -305,9 +314,8 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
   fetch(0);
   if (two_pass) {
     // The gate of clamp(sum) and the slope of the encode.  With the forward launch's output at hand both are read off it
-    // (single pass) - except where that output sits at the clamp's upper end: encode(1) is also what a sum above 1 and
-    // the one or two fp32 sums just below 1 produce, and torch.clamp passes the gradient AT 1 (inclusive), so those
-    // texels - and only those - recompute the summed image like the two-pass path (PBR_BOUNDARY_RECOMPUTE).
+    // (single pass) - except where that output does not determine them (at_boundary: the clamp's upper end, the knee of
+    // the sRGB curve): those texels - and only those - recompute the summed image like the two-pass path.
     V outv[3][N], slope[3][N];
     bool recompute = true;
     if (saved_out.have()) {
@@ -319,7 +327,7 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           slope[c][i] = encode_slope_from_out(outv[c][i], F.return_srgb);
-          if (kBoundaryRecompute) recompute = recompute || any_ge(outv[c][i], top);
+          if (kBoundaryRecompute) recompute = recompute || at_boundary(outv[c][i], top, F.return_srgb);
         }
     }
     if (recompute) {

@@ -1116,7 +1116,8 @@ def test_adjust_normal_strength_and_packing_on_cuda_maps():
     assert bool(((packed.cpu() - exp).abs() <= 3e-7 * exp.abs() + 1e-7).all())
     full = mat.as_tensor()
     assert full.shape[0] == 8
-    back = BasecolorMetallicMaterial.from_tensor(full, names=[("albedo", 3), ("normal", 3), ("roughness", 1), ("metallic", 1)], device=DEV)
+    order = [(k, t.shape[0]) for k, t in mat._maps.items()]   # as_tensor() without names stacks in the registry's order
+    back = BasecolorMetallicMaterial.from_tensor(full, names=order, device=DEV)
     for k in ("albedo", "roughness", "metallic"):
         assert torch.equal(back._maps[k], mat._maps[k]) and back._maps[k].data_ptr() != mat._maps[k].data_ptr()
     rgb = torch.rand(2 + 3, 20, 28, generator=g)

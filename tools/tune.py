@@ -55,6 +55,8 @@ d.view, d.lights, d.intensity = (ctypes.cast(x, ctypes.c_void_p) for x in (hv, h
 d.out, d.out_sl = _out_plane(out, bool(PER_LIGHT), True)
 g = _cabi.PbrCtGrads()
 g.grad_out, g.grad_out_sl = _out_plane(go, bool(PER_LIGHT), True)
+if L > 1 and not PER_LIGHT and int(os.environ.get("TUNE_FWD_OUT", 1)):
+    g.fwd_out = _out_plane(out, False, True)[0]   # one-pass accumulate backward from the forward launch's output (what autograd hands over)
 loss_buf = torch.zeros(1, device=dev)
 ls = _cabi.PbrCtLoss()
 ls.target, ls.target_sl = _out_plane(go, bool(PER_LIGHT), True)
