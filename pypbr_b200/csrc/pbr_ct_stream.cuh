@@ -285,10 +285,9 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_FWD_MIN_CTAS) ct_fo
   bool any = false;
 #pragma unroll
   for (int j = 0; j < kSSlots; ++j) { act[j] = slot_active(w, j, p.W); any = any || act[j]; }
-  // output address = uniform 64-bit base (plane pointer + batch and channel strides, the same for the whole CTA: uniform
-  // datapath) + ONE 32-bit per-thread offset (the host checked that in-plane offsets fit 32 bits): one instruction per
-  // store address instead of a 64-bit multiply-add chain
-  const int o_off = w.row * (int)p.out.sh + w.col;
+  // output pointer of material b0 at slot 0; advanced by one batch stride per tile (strides sit in the
+  // __grid_constant__ parameter block, i.e. the constant bank)
+  float* o = p.out.ptr + ((int64_t)b0 * p.out.sb + (int64_t)w.row * p.out.sh + w.col);
 
   for (int k = 0; k < ntiles; ++k) {
     const int s = k % kStages;
@@ -338,9 +337,10 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_FWD_MIN_CTAS) ct_fo
       for (int j = 0; j < G; ++j)
         if (act[j]) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) stg_v(p.out.ptr + ((int64_t)(b0 + k) * p.out.sb + (int64_t)c * p.out.sc) + (o_off + j * w.slot_stride), outv[c][j]);
+          for (int c = 0; c < 3; ++c) stg_v(o + c * p.out.sc + j * w.slot_stride, outv[c][j]);
         }
     }
+    o += p.out.sb;
     // producer: by the time warp 0 has shaded tile k every warp has long since read stage s
     if (!kPerWarp && tid < 32 && k + kStages < ntiles) {
       mbar_wait(&sh.empty[s], (k / kStages) & 1);
@@ -401,11 +401,11 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_ba
   LightGeomT<V> hg[kSSlots];
   stream_coords<kLight>(S, w, p.W, x, y, hg);
   const bool has_normal = p.normal.ptr != nullptr;
-  // gradient addresses: uniform 64-bit base per (tile, plane, channel) + one 32-bit per-thread offset per plane (see the forward)
-  const bool w_a = p.d_albedo.ptr != nullptr, w_n = has_normal && p.d_normal.ptr != nullptr, w_r = p.d_roughness.ptr != nullptr,
-             w_m = p.d_metspec.ptr != nullptr;
-  const int off_a = w.row * (int)p.d_albedo.sh + w.col, off_n = w.row * (int)p.d_normal.sh + w.col,
-            off_r = w.row * (int)p.d_roughness.sh + w.col, off_m = w.row * (int)p.d_metspec.sh + w.col;
+  // gradient pointers of material b0 at slot 0; advanced by one batch stride per tile
+  float* o_a = p.d_albedo.ptr ? p.d_albedo.ptr + ((int64_t)b0 * p.d_albedo.sb + (int64_t)w.row * p.d_albedo.sh + w.col) : nullptr;
+  float* o_n = (has_normal && p.d_normal.ptr) ? p.d_normal.ptr + ((int64_t)b0 * p.d_normal.sb + (int64_t)w.row * p.d_normal.sh + w.col) : nullptr;
+  float* o_r = p.d_roughness.ptr ? p.d_roughness.ptr + ((int64_t)b0 * p.d_roughness.sb + (int64_t)w.row * p.d_roughness.sh + w.col) : nullptr;
+  float* o_m = p.d_metspec.ptr ? p.d_metspec.ptr + ((int64_t)b0 * p.d_metspec.sb + (int64_t)w.row * p.d_metspec.sh + w.col) : nullptr;
   V loss_pair = splat<V>(0.0f);
   float gi_local[3] = {0.0f, 0.0f, 0.0f};
 
@@ -470,19 +470,18 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_ba
         ct_backward_group<WF, kLight, V, 1>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm);
 #endif
         const int jo = j * w.slot_stride;
-        const int64_t bk = b0 + k;
-        if (w_a) {
+        if (o_a) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) stg_v(p.d_albedo.ptr + (bk * p.d_albedo.sb + (int64_t)c * p.d_albedo.sc) + (off_a + jo), da[c][0]);
+          for (int c = 0; c < 3; ++c) stg_v(o_a + c * p.d_albedo.sc + jo, da[c][0]);
         }
-        if (w_n) {
+        if (o_n) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) stg_v(p.d_normal.ptr + (bk * p.d_normal.sb + (int64_t)c * p.d_normal.sc) + (off_n + jo), dn[c][0]);
+          for (int c = 0; c < 3; ++c) stg_v(o_n + c * p.d_normal.sc + jo, dn[c][0]);
         }
-        if (w_r) stg_v(p.d_roughness.ptr + bk * p.d_roughness.sb + (off_r + jo), dr[0]);
-        if (w_m) {
+        if (o_r) stg_v(o_r + jo, dr[0]);
+        if (o_m) {
 #pragma unroll
-          for (int c = 0; c < SL::mc; ++c) stg_v(p.d_metspec.ptr + (bk * p.d_metspec.sb + (int64_t)c * p.d_metspec.sc) + (off_m + jo), dm[c][0]);
+          for (int c = 0; c < SL::mc; ++c) stg_v(o_m + c * p.d_metspec.sc + jo, dm[c][0]);
         }
       }
     }
@@ -491,6 +490,10 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_ba
       fence_proxy_async();
       warp_issue(sh, &full[s], my_stages + s * my_stage_floats, b0 + k + kStages, threadIdx.y, w.wcol, w.seg_bytes, policy);
     }
+    if (o_a) o_a += p.d_albedo.sb;
+    if (o_n) o_n += p.d_normal.sb;
+    if (o_r) o_r += p.d_roughness.sb;
+    if (o_m) o_m += p.d_metspec.sb;
     // producer: by the time warp 0 has shaded tile k every warp has long since read stage s
     if (!kPerWarp && tid < 32 && k + kStages < ntiles) {
       mbar_wait(&sh.empty[s], (k / kStages) & 1);
