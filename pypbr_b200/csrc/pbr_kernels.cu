@@ -464,7 +464,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 #ifndef PBR_BWD_CACHED_MIN_CTAS
 #define PBR_BWD_CACHED_MIN_CTAS 2
 #endif
-constexpr int bwd_min_ctas(int light_mode) { return light_mode == kLightPointCached ? PBR_BWD_CACHED_MIN_CTAS : PBR_BWD_MIN_CTAS; }
+constexpr int bwd_min_ctas(int light_mode) {
+  return (light_mode == kLightPointCached || light_mode == kLightPointCachedAllBig) ? PBR_BWD_CACHED_MIN_CTAS : PBR_BWD_MIN_CTAS;
+}
 
 // The saved forward output of the row segment being back-propagated (PbrCtGrads.fwd_out).  It travels through slot 1 of
 // the thread's cp.async ring (accumulate mode keeps only slot 0 busy, with grad_out), requested together with grad_out
@@ -1141,21 +1143,32 @@ static bool geom_cache_disabled() {
   return off;
 }
 
-static int light_mode(const CtKParams& k) {
+#ifndef PBR_GC_BIG_MAX_LIGHTS
+#define PBR_GC_BIG_MAX_LIGHTS 8   // backward, 4 < L <= 8: all 8 fields cached, full register budget (2 CTAs per SM by registers anyway)
+#endif
+static int light_mode(const CtKParams& k, bool backward) {
   if (!k.flags.point) return kLightDirectional;
-  if (k.d_lights || k.d_view) return kLightPoint;   // geometry gradients need the per-texel intermediates
   if (!k.vec_fast) return kLightPoint;              // the element-access flavour only exists for the uncached light modes
+  if (k.d_lights || k.d_view) {
+    // geometry gradients (shared parameters of a fit with unknown lighting): the 6-field cache when a walk over several
+    // materials pays for it, else the per-texel geometry
+    if (backward && k.flags.L > 1 && k.B >= 2 && !geom_cache_disabled() &&
+        geom_cache_bytes(k.flags.L, kLightPointCached) <= (size_t)PBR_GC_MAX_BYTES) return kLightPointCached;
+    return kLightPoint;
+  }
   if (k.flags.L == 1) return kLightPointHoisted;
   if (k.B >= 2 && !geom_cache_disabled()) {
     if (k.flags.L <= PBR_GC_ALL_MAX_LIGHTS) return kLightPointCachedAll;
+    // (not under the Adam epilogue: with its 30 KB of staging the two CTAs would leave the SM almost no L1, 12.21 -> 12.35 ms on C5)
+    if (backward && !k.adam_on && k.flags.L <= PBR_GC_BIG_MAX_LIGHTS) return kLightPointCachedAllBig;
     if (geom_cache_bytes(k.flags.L, kLightPointCached) <= (size_t)PBR_GC_MAX_BYTES) return kLightPointCached;
   }
   return kLightPoint;
 }
 
-static void ct_launch_shape(CtKParams& k, dim3& grid, dim3& block) {
+static void ct_launch_shape(CtKParams& k, dim3& grid, dim3& block, bool backward) {
   launch_shape(k.B, k.H, k.W, grid, block, kCtThreads, kCtTexels);
-  const int lm = light_mode(k);
+  const int lm = light_mode(k, backward);
   k.mats_per_cta = (lm == kLightPointHoisted || is_cached(lm)) ? (k.B < kHoistMats ? k.B : kHoistMats) : 1;
   grid.z = (k.B + k.mats_per_cta - 1) / k.mats_per_cta;
 }
@@ -1182,7 +1195,7 @@ static int kernel_workflow(const PbrCtDesc* d) {
 
 template <int WF>
 static void launch_fwd(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t st) {
-  const int lm = light_mode(k);
+  const int lm = light_mode(k, false);
   if (!k.vec_fast) {   // any alignment / ragged width: element accesses, uncached light modes
     if (lm == kLightDirectional) ct_forward_kernel<WF, kLightDirectional, false><<<grid, block, 0, st>>>(k);
     else ct_forward_kernel<WF, kLightPoint, false><<<grid, block, 0, st>>>(k);
@@ -1203,13 +1216,14 @@ constexpr size_t kAdamSmemBytes = (size_t)30 * kCtThreads * kCtTexels * sizeof(f
 template <int WF>
 static void launch_bwd(const CtKParams& k_in, dim3 grid, dim3 block, cudaStream_t st) {
   CtKParams k = k_in;
-  const int lm = light_mode(k);
+  const int lm = light_mode(k, true);
   const size_t cache = is_cached(lm) ? geom_cache_bytes(k.flags.L, lm) : 0;
   k.adam_smem_off = (int)cache;
   const size_t smem = cache + (k.adam_on ? kAdamSmemBytes : 0);
   if (k.d_lights || k.d_view) {   // geometry gradients: the uncached per-texel light modes
     if (k.vec_fast) {
-      if (k.flags.point) launch_dyn<ct_backward_kernel<WF, kLightPoint, true>>(k, grid, block, smem, st);
+      if (lm == kLightPointCached) launch_dyn<ct_backward_kernel<WF, kLightPointCached, true>>(k, grid, block, smem, st);
+      else if (k.flags.point) launch_dyn<ct_backward_kernel<WF, kLightPoint, true>>(k, grid, block, smem, st);
       else launch_dyn<ct_backward_kernel<WF, kLightDirectional, true>>(k, grid, block, smem, st);
     } else {
       if (k.flags.point) launch_dyn<ct_backward_kernel<WF, kLightPoint, true, false>>(k, grid, block, smem, st);
@@ -1227,6 +1241,7 @@ static void launch_bwd(const CtKParams& k_in, dim3 grid, dim3 block, cudaStream_
     case kLightPoint: launch_dyn<ct_backward_kernel<WF, kLightPoint>>(k, grid, block, smem, st); break;
     case kLightPointCached: launch_dyn<ct_backward_kernel<WF, kLightPointCached>>(k, grid, block, smem, st); break;
     case kLightPointCachedAll: launch_dyn<ct_backward_kernel<WF, kLightPointCachedAll>>(k, grid, block, smem, st); break;
+    case kLightPointCachedAllBig: launch_dyn<ct_backward_kernel<WF, kLightPointCachedAllBig>>(k, grid, block, smem, st); break;
     default: launch_dyn<ct_backward_kernel<WF, kLightPointHoisted>>(k, grid, block, smem, st); break;
   }
 }
@@ -1357,7 +1372,7 @@ static int ct_dispatch(CtKParams& k, int wf, bool backward, cudaStream_t st) {
     else stream = fits_i32(k.out, k.H, k.W);
   }
   if (stream) k.mats_per_cta = mats;
-  else ct_launch_shape(k, grid, block);
+  else ct_launch_shape(k, grid, block, backward);
   switch (wf) {
     case 0: launch_wf0(k, grid, block, stream, backward, st); break;
     case 1: launch_wf1(k, grid, block, stream, backward, st); break;

@@ -88,12 +88,17 @@ enum LightMode {
   kLightPointCached = 3,  // point lights, L > 1: the caller computes the geometry of every light once per
                           // texel, parks it in its own shared-memory slots (GeomCache) and the light loops
                           // of all the materials it walks over read it back.  Caches l and h (6 fields).
-  kLightPointCachedAll = 4  // same with all 8 fields cached: for few lights, where the cache does not cost occupancy
+  kLightPointCachedAll = 4,  // same with all 8 fields cached: for few lights, where the cache does not cost occupancy
+  kLightPointCachedAllBig = 5   // all 8 fields, backward with the full register budget: 4 < L <= 8, where 2 CTAs per SM still fit
+                                // (loss kernel at L = 8: 2.73 -> 2.68 ms per 32 x 1024^2, profiles/r2_tune_*.json)
 };
-PBR_HDC bool is_cached(int light_mode) { return light_mode == kLightPointCached || light_mode == kLightPointCachedAll; }
+// (Tried and dropped: caching h only - 3 fields - for the forward of many lights, so that the cache leaves room for 4 CTAs per
+// SM instead of 2: l and the attenuation recomputed per light cost more than the occupancy gave back, 0.824 -> 0.912 ms at
+// L = 16: that kernel is bound by the FP32 pipe, not by latency.)
+PBR_HDC bool is_cached(int light_mode) { return light_mode >= kLightPointCached && light_mode <= kLightPointCachedAllBig; }
 // Fields: l (3), h (3) [, p5, att].  The fields that are not cached are recomputed from the plane position
 // (they live in the tolerant zone; l and h feed N.L / N.H and stay bit-exact).
-PBR_HDC int geom_fields(int light_mode) { return light_mode == kLightPointCachedAll ? 8 : 6; }
+PBR_HDC int geom_fields(int light_mode) { return (light_mode == kLightPointCachedAll || light_mode == kLightPointCachedAllBig) ? 8 : 6; }
 
 // Per-thread geometry cache (kLightPointCached).  Field f of light l of lane-value i lives at
 // base[(l * kGeomFields + f) * fstride + i * stride]; `base` already points at the calling thread's slot,
@@ -290,8 +295,8 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
                               GeomCache<V> gc = GeomCache<V>(), GeomSink geom_sink = GeomSink(),
                               SavedOut saved_out = SavedOut()) {
   constexpr bool kGeom = GeomSink::kOn;
-  static_assert(!kGeom || kLight == kLightDirectional || kLight == kLightPoint,
-                "geometry gradients run on the uncached per-texel light modes");
+  static_assert(!kGeom || kLight == kLightDirectional || kLight == kLightPoint || kLight == kLightPointCached,
+                "geometry gradients: directional, per-texel point lights, or the 6-field geometry cache");
   V g_view[kGeom ? N : 1][3];
   if (kGeom) {
 #pragma unroll
@@ -404,7 +409,7 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
       for (int c = 0; c < 3; ++c) gi_sum[c] += lane_sum(gi[c]);
       if (kGeom) {
         V glt[3];
-        light_geom_bwd<kLight == kLightPoint>(g[i], gg, S.light[l].p, x[i], y, S.vx, S.vy, S.vz, glt, g_view[i]);
+        light_geom_bwd<kLight != kLightDirectional>(g[i], gg, S.light[l].p, x[i], y, S.vx, S.vy, S.vz, glt, g_view[i]);
 #pragma unroll
         for (int c = 0; c < 3; ++c) glt_sum[c] += lane_sum(glt[c]);
       }

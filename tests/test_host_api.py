@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_cabi.lib_path())
     for name in declared:
         assert hasattr(lib, name), name
-    assert _cabi.load().pbr_abi_version() == _cabi.ABI_VERSION == 4
+    assert _cabi.load().pbr_abi_version() == _cabi.ABI_VERSION == 5
 
 
 def test_struct_layouts_match_header_sizes():
@@ -264,3 +264,52 @@ def test_loss_allreduce_world2_gloo():
         p.join(timeout=60)
     expect = torch.arange(70, dtype=torch.float32).view(10, 7).sum(0).tolist()
     assert res[0] == expect and res[1] == expect
+
+
+def _gloo_async_worker(rank, world, port, q):
+    """The side-stream loss all-reduce of the one-launch fit step, on CPU tensors (gloo): PendingLoss.wait() / .item() deliver
+    the reduced buffer, and the two-slot ring never hands out a buffer whose all-reduce is still pending."""
+    import torch.distributed as dist
+    from pypbr_b200.fit import PendingLoss, allreduce_loss_async
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    out = []
+    pend = [None, None]
+    for step in range(5):
+        i = step % 2
+        if pend[i] is not None:
+            pend[i].wait()
+        buf = torch.full((7,), float(rank + 1 + step))
+        pend[i] = allreduce_loss_async(buf, scale=0.5)
+        assert isinstance(pend[i], PendingLoss)
+        out.append(pend[i])
+    vals = [p.item() for p in out]
+    bufs = [p.wait().tolist() for p in out]
+    q.put((rank, vals, bufs))
+    dist.destroy_process_group()
+
+
+def test_async_loss_allreduce_world2_gloo():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_async_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r: (v, b) for r, v, b in (q.get(timeout=120) for _ in procs)}
+    for p in procs:
+        p.join(timeout=60)
+    for step in range(5):
+        total = (1 + step) + (2 + step)
+        for r in (0, 1):
+            assert res[r][0][step] == total * 0.5 and res[r][1][step] == [float(total)] * 7
+
+
+def test_pending_loss_without_a_process_group_is_the_local_buffer():
+    from pypbr_b200.fit import allreduce_loss_async
+
+    buf = torch.tensor([3.0, 1.0])
+    p = allreduce_loss_async(buf, scale=2.0)
+    assert p.wait() is buf and p.item() == 6.0

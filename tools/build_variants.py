@@ -47,6 +47,7 @@ VARIANTS = {
     # round 2
     "r2_noenc": v(encode_diet=0),               # sRGB encode on the shading path with the clamps / guards that cannot bind
     "r2_nobr": v(boundary_recompute=0),         # one-pass accumulate backward without the boundary recompute
+    "r2_nobig": v(gc_big_max_lights=0),         # backward, 4 < L <= 8: 6-field cache instead of all 8 fields
     "r2_sb4": v(stream_bwd_min_ctas=4),         # streamed backward capped at 128 registers (4 CTAs per SM)
     "r2_sf5": v(stream_fwd_min_ctas=5),         # streamed forward capped at 102 registers (5 CTAs per SM)
     # memory pipeline only (no shading math): the floor of the TMA-in / STG-out design
