@@ -273,12 +273,33 @@ def plane(t: Optional[torch.Tensor]) -> PbrPlane:
     """(C,H,W) or (B,C,H,W) tensor -> PbrPlane (strides in elements).  None -> NULL plane."""
     if t is None:
         return PbrPlane(None, 0, 0, 0)
-    assert t.stride(-1) == 1 or t.shape[-1] == 1, "call rowmajor() first"
-    if t.dim() == 3:
-        return PbrPlane(t.data_ptr(), 0, t.stride(0), t.stride(1))
-    if t.dim() == 4:
-        return PbrPlane(t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
+    st = t.stride()
+    n = len(st)
+    assert st[-1] == 1 or t.shape[-1] == 1, "call rowmajor() first"
+    if n == 3:
+        return PbrPlane(t.data_ptr(), 0, st[0], st[1])
+    if n == 4:
+        return PbrPlane(t.data_ptr(), st[0], st[1], st[2])
     raise ValueError(f"maps must be (C,H,W) or (B,C,H,W), got shape {tuple(t.shape)}")
+
+
+class device_guard:
+    """`with torch.cuda.device(dev)` only when `dev` is not already current (the context manager costs ~5 us per entry,
+    a tenth of a small-image call)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev: torch.device):
+        idx = dev.index
+        self.ctx = None if (idx is None or idx == torch.cuda.current_device()) else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
 
 
 def touch(*tensors) -> None:

@@ -111,7 +111,7 @@ class _CookTorranceFn(torch.autograd.Function):
         d = _fill_desc(cfg, albedo, normal, roughness, metspec, keep)
         out = torch.empty(_out_shape(cfg, albedo), dtype=torch.float32, device=albedo.device)
         d.out, d.out_sl = _out_plane(out, cfg.per_light, cfg.batched)
-        with torch.cuda.device(albedo.device):
+        with _cabi.device_guard(albedo.device):
             _cabi.check(lib.pbr_ct_forward(_cabi.byref(d), _cabi.stream_ptr(albedo.device)), "pbr_ct_forward")
         ctx.cfg = cfg
         ctx.has_normal = normal is not None
@@ -155,7 +155,7 @@ class _CookTorranceFn(torch.autograd.Function):
         d_view = torch.zeros(3, dtype=torch.float32, device=dev) if need[7] else None
         g.d_lights = d_lights.data_ptr() if d_lights is not None else None
         g.d_view = d_view.data_ptr() if d_view is not None else None
-        with torch.cuda.device(dev):
+        with _cabi.device_guard(dev):
             _cabi.check(lib.pbr_ct_backward(_cabi.byref(d), _cabi.byref(g), _cabi.stream_ptr(dev)), "pbr_ct_backward")
         shared = []
         for t, meta in zip((d_int, d_lights, d_view), ctx.leaf_meta):
@@ -194,10 +194,14 @@ def _prepare(material: MaterialBase, device, view_dir, light, intensity, light_t
             f"pypbr_b200: CookTorranceBRDF runs on CUDA only (material.device is {device}); there is no CPU fallback. "
             "Use material.to('cuda') or CookTorranceBRDF(override_device='cuda')."
         )
-    roughness = roughness.to(device)
-    normal = normal.to(device) if normal is not None else None
-    metspec = metspec.to(device)
-    albedo = albedo.to(device)
+    # the reference moves every map with .to(device) on every call (cooktorrance.py:99-112); a map that is already there is
+    # handed on untouched (Tensor.to would return it as well, several microseconds later)
+    want = device.index if device.index is not None else torch.cuda.current_device()
+
+    def mv(t):
+        return t if (t is None or (t.is_cuda and t.device.index == want)) else t.to(device)
+
+    roughness, normal, metspec, albedo = mv(roughness), mv(normal), mv(metspec), mv(albedo)
     cfg.albedo_is_srgb = bool(material.albedo_is_srgb)
 
     for name, t in (("albedo", albedo), ("roughness", roughness), ("normal", normal), ("metallic/specular", metspec)):
@@ -258,9 +262,15 @@ def _prepare(material: MaterialBase, device, view_dir, light, intensity, light_t
     all_dev = all(t.is_cuda and t.device == device for t in (view, lights, inten))
     cfg.on_device = all_dev
     if all_dev:
-        cfg.view = view.detach().reshape(3).to(torch.float32).contiguous()
-        cfg.lights = lights.detach().to(torch.float32).contiguous()
-        cfg.intensity = inten.detach().to(torch.float32).contiguous()
+        def f32c(t):
+            t = t.detach()
+            if t.dtype != torch.float32:
+                t = t.to(torch.float32)
+            return t if t.is_contiguous() else t.contiguous()
+
+        cfg.view = f32c(view).reshape(3)
+        cfg.lights = f32c(lights)
+        cfg.intensity = f32c(inten)
     else:  # small host arrays are copied into the kernel launch parameters: no H2D copy, no sync for CPU inputs
         cfg.view = view.detach().reshape(3).to(torch.float32).cpu().tolist()
         cfg.lights = lights.detach().to(torch.float32).cpu().reshape(-1).tolist()

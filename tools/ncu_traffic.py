@@ -23,5 +23,10 @@ for arg in sys.argv[1:]:
                                 "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                                 "warp_instructions": num("smsp__inst_executed.sum"),
                                 "source": f"ncu --set full, {os.path.basename(path)} (profiles/)"}
+# the hash of the kernel sources the captures were taken from, written on the GPU box by tools/gpu_prof_r2.sh at capture time:
+# bench.py only reports `roofline.traffic` while the sources it is built from still hash to this
+stamp = os.path.join(ROOT, "gpurun_out", "csrc_sha16.txt")
+if os.path.exists(stamp):
+    out["_csrc_sha16"] = open(stamp).read().strip()
 json.dump(out, open(out_path, "w"), indent=1)
 print(json.dumps(out, indent=1))
