@@ -502,8 +502,11 @@ def measure_shading(name, args, ctx, steps, warmup):
                 if record:
                     bwd_ms.append((e0, e1))
                 return
+            # --shared-grads: the fit with unknown lighting - intensity, light position and view gradients ride along
+            # (PbrCtGrads.d_intensity / d_lights / d_view; 1 + 6L + 3 floats to all-reduce instead of 1 + 3L)
             buf, grads = fused_loss_step(mat, target, view, lights, inten, "point", 1.0, multi_light="per_light",
-                                         loss_scale=1.0 / (target.numel() * world), out=bufs)
+                                         loss_scale=1.0 / (target.numel() * world), out=bufs,
+                                         want_intensity_grad=args.shared_grads, want_geometry_grad=args.shared_grads)
             e1.record()
             allreduce_loss_and_shared(buf)
             adam.step({k: grads[k] for k in adam.params})
@@ -552,7 +555,8 @@ def measure_shading(name, args, ctx, steps, warmup):
         kname = "ct_backward_kernel<0,3,0> (fused loss + Adam epilogue, cached light geometry)"
     elif fused_fit:
         kbytes = texels * (32 + 12 * L + 32)
-        kname = "ct_backward_kernel<0,3,0> (fused loss, cached light geometry)"
+        kname = "ct_backward_kernel<0,5,0> (fused loss, cached light geometry)" if not args.shared_grads else \
+                "ct_backward_kernel<0,3,1> (fused loss + d_intensity / d_lights / d_view, cached light geometry)"
     else:
         fwd_avg = sum(a.elapsed_time(b) for a, b in fwd_ms) / len(fwd_ms)
         # accumulate mode with several lights: + the forward output the one-pass backward reads (12 B per texel)
@@ -582,7 +586,7 @@ def measure_shading(name, args, ctx, steps, warmup):
     res = {
         "value": value, "unit": UNIT, "ms_per_step": elapsed_ms / steps, "steps": steps, "warmup": warmup,
         "config": {"workload": cfg["workload"], "per_gpu_batch": B, "H": H, "W": W, "lights": L,
-                   "mode": ("per_light fused loss + Adam, " + args.fit) if fused_fit else "accumulate", "parallelism": f"batch-shard x{world}",
+                   "mode": ("per_light fused loss + Adam, " + args.fit + (", shared-parameter gradients" if args.shared_grads else "")) if fused_fit else "accumulate", "parallelism": f"batch-shard x{world}",
                    "l2": f"inputs ({texels * 32 / 1e9:.1f} GB per GPU) exceed the 126 MB L2; no flush needed"},
         "roofline": roofline, "gpu_launches": int(launches), "clocks": clk.summary(),
     }
@@ -594,7 +598,9 @@ def measure_shading(name, args, ctx, steps, warmup):
         res["allreduce"] = {
             "collective": f"NCCL all_reduce(SUM) of {1 + 3 * L} floats per step" + ("" if world > 1 else " (single rank: no-op)"),
             "where": "side stream behind an event; the compute stream never waits for it" if async_loss else "compute stream (blocking)",
-            "ms_per_step": ar, "world": world}
+            # from the fit kernel's completion to the reduced loss: includes waiting for the slowest rank's kernel and for an SM
+            # slot under the NEXT step's kernel, which is already running - it is off the critical path by construction
+            "completion_latency_ms": ar, "world": world}
         if last[0] is not None and async_loss:
             res["loss"] = last[0].item()
     return res
@@ -1137,6 +1143,8 @@ def main():
     ap.add_argument("--fit", default="one-launch", choices=["one-launch", "one-launch-sync", "two-kernel"],
                     help="c5: pbr_ct_fit_step with the loss all-reduce on a side stream (default) or on the compute stream, "
                          "or pbr_ct_loss_fwd_bwd + pbr_adam_step")
+    ap.add_argument("--shared-grads", action="store_true",
+                    help="c5 --fit two-kernel: also d(light intensity, light position, view direction), the fit with unknown lighting")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-eager", action="store_true")

@@ -48,6 +48,12 @@ VARIANTS = {
     "r2_noenc": v(encode_diet=0),               # sRGB encode on the shading path with the clamps / guards that cannot bind
     "r2_nobr": v(boundary_recompute=0),         # one-pass accumulate backward without the boundary recompute
     "r2_nobig": v(gc_big_max_lights=0),         # backward, 4 < L <= 8: 6-field cache instead of all 8 fields
+    "r2_bpw": v(stream_per_warp_bwd=1),                                # streamed backward: per-warp copy pipelines, refill after the last read
+    "r2_bpw_late": v(stream_per_warp_bwd=1, stream_bwd_late_refill=1), # ... refill after the tile
+    "r2_st3": v(stream_stages=3),                                      # three stages (CTA-level backward, per-warp forward)
+    "r2_bpw_st3": v(stream_per_warp_bwd=1, stream_stages=3),
+    "r2_hm22": v(hoist_mats=22),                                       # 22 materials per CTA walk: 3 chunks of a 64-material batch
+    "r2_hm32": v(hoist_mats=32),
     "r2_sb4": v(stream_bwd_min_ctas=4),         # streamed backward capped at 128 registers (4 CTAs per SM)
     "r2_sf5": v(stream_fwd_min_ctas=5),         # streamed forward capped at 102 registers (5 CTAs per SM)
     # memory pipeline only (no shading math): the floor of the TMA-in / STG-out design
