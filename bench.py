@@ -333,13 +333,11 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def run_reference_c4(args, threads):
+def c4_cpu_pipeline(H, W):
     """BASELINE.json configs[3] on the host: the port's conversions + blends (oracle/pbr_oracle.py restates
-    metallic.py:90-109 and blending/functional.py:64-196 op for op).  Bounded sample: the same pipeline at 2048x2048
-    (a quarter of the texels; every op is per-texel, cost is linear in the texel count)."""
+    metallic.py:90-109 and blending/functional.py:64-196 op for op).  Returns a callable running one pipeline."""
     from oracle import pbr_oracle as O
 
-    H = W = 2048
     mats = []
     for seed in (4001, 4002):
         m = {k: v[0] for k, v in synth_maps(1, H, W, torch.device("cpu"), seed).items()}
@@ -359,6 +357,32 @@ def run_reference_c4(args, threads):
         b2["normal"] = O.process_normal_map(b2["normal"])
         return b1, b2
 
+    return pipeline
+
+
+C4_SAMPLE_HW = 2048   # bounded sample: a quarter of the 4096 x 4096 texels (every op is per-texel: cost is linear in the texel count)
+
+
+def c4_cpu_sample(reps=1):
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    pipe = c4_cpu_pipeline(C4_SAMPLE_HW, C4_SAMPLE_HW)
+    pipe()
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        pipe()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": C4_SAMPLE_HW * C4_SAMPLE_HW / best / 1e9, "unit": "Gtexel/s", "cores": threads, "kind": "port",
+            "sample": f"the same pipeline on two {C4_SAMPLE_HW}x{C4_SAMPLE_HW} materials (1/4 of the texels), best of {reps} after 1 warm-up "
+                      f"({best:.2f} s each); oracle/pbr_oracle.py"}
+
+
+def run_reference_c4(args, threads):
+    """--impl reference --config c4: the conversion + blend pipeline of the port on the host cores, a bounded sample per step."""
+    H = W = C4_SAMPLE_HW
+    pipeline = c4_cpu_pipeline(H, W)
     for _ in range(max(args.warmup, 1)):
         pipeline()
     t0 = time.perf_counter()
@@ -901,6 +925,16 @@ def run_ours(args):
                 r["gpu_eager_baseline"] = gpu_eager_baseline(k, ctx.dev, r["value"])
             cfgs[k] = r
             torch.cuda.empty_cache()
+        # the conversion + blend pipeline has no multi-GPU dimension (two materials): rank 0's GPU alone
+        if ctx.rank == 0:
+            c4 = run_c4(args, emit=False)
+            cfgs["c4"] = {"value": c4["value"], "unit": c4["unit"], "metric": c4["metric"], "ms_per_step": c4["ms_per_step"], "steps": c4["steps"],
+                          "warmup": c4["warmup"], "config": c4["config"], "roofline": c4["roofline"], "gpu_launches": c4["gpu_launches"],
+                          "clocks": c4["clocks"]}
+            if solo and not args.no_cpu:
+                cfgs["c4"]["cpu_baseline"] = c4_cpu_sample(reps=1)
+            torch.cuda.empty_cache()
+        ctx.barrier()
         line["configs"] = cfgs
     if ctx.rank == 0:
         print(json.dumps(line), flush=True)
@@ -908,7 +942,7 @@ def run_ours(args):
 
 
 # ---------------------------------------------------------------------------------------------- config 4
-def run_c4(args):
+def run_c4(args, emit=True):
     """
     BASELINE.json configs[3] (SURVEY.md §8d "C4"): two 4096x4096 metallic materials (albedo, normal, roughness,
     metallic, height) -> to_diffuse_specular_material() on each -> blend_materials(d1, d2, "mask", mask) ->
@@ -1043,6 +1077,10 @@ def run_c4(args):
                      "pipeline_frac": total_bytes / (pipe_ms * 1e-3) / 1e9 / peak, "kernels": kernels},
         "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clk.summary(),
     }
+    if not emit:
+        return line
+    if not args.no_cpu:
+        line["cpu_baseline"] = c4_cpu_sample(reps=1)
     print(json.dumps(line), flush=True)
 
 

@@ -304,15 +304,21 @@ typedef struct PbrAdamDesc {
  *                g = (-Nx, -Ny | +Ny) / (Nz + 1e-8) * scale (flip_y as above) and its forward-difference divergence with
  *                replicate padding.  `in` has 3 channels, `out` ONE channel; in and out must not overlap.  The Poisson
  *                solve that follows (utils/functions.py:286-323) is two FFT library calls and stays with the caller.
+ *   FROM_HEIGHT_BWD: the adjoint of FROM_HEIGHT (the reference's op sequence is differentiable, so a height map can be fitted
+ *                through the normals it induces): `in` = the height map (1 ch), `aux` = the gradient w.r.t. the 3-channel normal
+ *                map, `out` = the gradient w.r.t. the height map (1 ch):
+ *                d_h[y,x] = scale * (a[y,x+1] - a[y,x-1] + b[y+1,x] - b[y-1,x]) with a = -g_u.x, b = -+g_u.y of the neighbour texel,
+ *                g_u the gradient pushed through that texel's normalisation (recomputed), zero outside the image.
  */
-enum { PBR_NORMAL_OP_ROTATE = 0, PBR_NORMAL_OP_FROM_HEIGHT = 1, PBR_NORMAL_OP_DIVERGENCE = 2 };
+enum { PBR_NORMAL_OP_ROTATE = 0, PBR_NORMAL_OP_FROM_HEIGHT = 1, PBR_NORMAL_OP_DIVERGENCE = 2, PBR_NORMAL_OP_FROM_HEIGHT_BWD = 3 };
 typedef struct PbrNormalOpDesc {
   int32_t B, H, W;
   int32_t op;               /* PBR_NORMAL_OP_* */
   float cos_a, sin_a;       /* ROTATE */
   float scale;              /* FROM_HEIGHT, DIVERGENCE */
   int32_t flip_y;           /* FROM_HEIGHT, DIVERGENCE: 1 = NormalConvention.DIRECTX */
-  PbrPlane in, out;         /* out: 3 ch (DIVERGENCE: 1 ch) */
+  PbrPlane in, out;         /* out: 3 ch (DIVERGENCE, FROM_HEIGHT_BWD: 1 ch) */
+  PbrPlane aux;             /* FROM_HEIGHT_BWD: gradient w.r.t. the normal map (3 ch); otherwise unused */
 } PbrNormalOpDesc;
 
 /*

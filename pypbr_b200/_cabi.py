@@ -167,11 +167,11 @@ class PbrNormalOpDesc(Structure):
     _fields_ = [
         ("B", c_int32), ("H", c_int32), ("W", c_int32), ("op", c_int32),
         ("cos_a", c_float), ("sin_a", c_float), ("scale", c_float), ("flip_y", c_int32),
-        ("in_", PbrPlane), ("out", PbrPlane),
+        ("in_", PbrPlane), ("out", PbrPlane), ("aux", PbrPlane),
     ]
 
 
-NORMAL_OP_ROTATE, NORMAL_OP_FROM_HEIGHT, NORMAL_OP_DIVERGENCE = 0, 1, 2
+NORMAL_OP_ROTATE, NORMAL_OP_FROM_HEIGHT, NORMAL_OP_DIVERGENCE, NORMAL_OP_FROM_HEIGHT_BWD = 0, 1, 2, 3
 
 # order = the `which` argument of pbr_sizeof()
 STRUCTS = (PbrPlane, PbrCtDesc, PbrCtGrads, PbrCtLoss, PbrConvDesc, PbrBlendMap, PbrBlendDesc, PbrColorDesc, PbrNormalDesc,

@@ -281,6 +281,42 @@ __global__ void __launch_bounds__(kThreads) normal_op_kernel(const __grid_consta
     store_seg<kTexels>(d.out.ptr + plane_off(d.out, w.b, 0, w.row, w.col0), w.vec, w.valid, div);
     return;
   }
+  if (d.op == PBR_NORMAL_OP_FROM_HEIGHT_BWD) {
+    // d_h[y][x] = scale * (a[y][x+1] - a[y][x-1] + b[y+1][x] - b[y-1][x]); a = -g_u.x, b = (flip_y ? +1 : -1) * g_u.y at the
+    // neighbour, g_u = the neighbour's normal gradient pushed through ITS normalisation (recomputed from the height map)
+    const float* hbase = d.in.ptr + plane_off(d.in, w.b, 0, 0, 0);
+    auto hat = [&](int y, int x) -> float { return (y >= 0 && y < d.H && x >= 0 && x < d.W) ? __ldg(hbase + (int64_t)y * d.in.sh + x) : 0.0f; };
+    // (a, b) of texel (y, x); zero outside the image
+    auto ab = [&](int y, int x, float& a, float& b) {
+      a = 0.0f; b = 0.0f;
+      if (y < 0 || y >= d.H || x < 0 || x >= d.W) return;
+      const float gx = (hat(y, x - 1) - hat(y, x + 1)) * d.scale, gy = (hat(y - 1, x) - hat(y + 1, x)) * d.scale;
+      const float u[3] = {-gx, d.flip_y ? gy : -gy, 1.0f};
+      float g[3], gu[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) g[c] = __ldg(d.aux.ptr + plane_off(d.aux, w.b, c, y, x));
+      normalize3_bwd(u, g, gu);
+      a = -gu[0];
+      b = d.flip_y ? gu[1] : -gu[1];
+    };
+    float dh[kTexels];
+    float a_prev, a_cur, b_dummy;
+    ab(w.row, w.col0 - 1, a_prev, b_dummy);
+    ab(w.row, w.col0, a_cur, b_dummy);
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i) {
+      const int x = w.col0 + i;
+      float a_next, b_up, b_dn, t;
+      ab(w.row, x + 1, a_next, t);
+      ab(w.row - 1, x, t, b_up);
+      ab(w.row + 1, x, t, b_dn);
+      dh[i] = d.scale * ((a_next - a_prev) + (b_dn - b_up));
+      a_prev = a_cur;
+      a_cur = a_next;
+    }
+    store_seg<kTexels>(d.out.ptr + plane_off(d.out, w.b, 0, w.row, w.col0), w.vec, w.valid, dh);
+    return;
+  }
   if (d.op == PBR_NORMAL_OP_ROTATE) {
     float v[3][kTexels];
 #pragma unroll

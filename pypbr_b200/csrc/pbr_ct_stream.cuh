@@ -467,7 +467,8 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_ba
         dr[0] = r[0];
         (void)gout; (void)int_sink;
 #else
-        ct_backward_group<WF, kLight, V, 1>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm);
+        ct_backward_group<WF, kLight, V, 1>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, NoFetch(), GeomCache<V>(),
+                                            NoGeomSink(), NoSavedOut(), kIntGrad);
 #endif
         const int jo = j * w.slot_stride;
         if (o_a) {

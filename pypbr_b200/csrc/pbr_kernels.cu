@@ -705,10 +705,10 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       gcs.base += s * gc.stride;
       if constexpr (kGeom) {
         ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs,
-                                            CtaGeomSink{s_geo, p.flags.L, tid, live}, CtaSavedOut{ring + 3 * (kCtThreads * NT), have_fout});
+                                            CtaGeomSink{s_geo, p.flags.L, tid, live}, CtaSavedOut{ring + 3 * (kCtThreads * NT), have_fout}, int_grad);
       } else {
         ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs,
-                                            NoGeomSink(), CtaSavedOut{ring + 3 * (kCtThreads * NT), have_fout});
+                                            NoGeomSink(), CtaSavedOut{ring + 3 * (kCtThreads * NT), have_fout}, int_grad);
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) { unpair_to<G>(da[c], s, d_albedo[c]); unpair_to<G>(dn[c], s, d_normal[c]); unpair_to<G>(dm[c], s, d_met[c]); }
@@ -1728,8 +1728,9 @@ int pbr_adam_step(const PbrAdamDesc* d, pbr_stream_t stream) {
 int pbr_normal_op(const PbrNormalOpDesc* d, pbr_stream_t stream) {
   if (!d) return PBR_E_NULL;
   if (int rc = check_dims(d->B, d->H, d->W)) return rc;
-  if (d->op < PBR_NORMAL_OP_ROTATE || d->op > PBR_NORMAL_OP_DIVERGENCE) return PBR_E_ENUM;
+  if (d->op < PBR_NORMAL_OP_ROTATE || d->op > PBR_NORMAL_OP_FROM_HEIGHT_BWD) return PBR_E_ENUM;
   if (!d->in.ptr || !d->out.ptr) return PBR_E_NULL;
+  if (d->op == PBR_NORMAL_OP_FROM_HEIGHT_BWD && !d->aux.ptr) return PBR_E_NULL;
   if (d->op != PBR_NORMAL_OP_ROTATE && d->in.ptr == d->out.ptr) return PBR_E_NULL;   // a stencil cannot run in place
   NormalOpKParams k{};
   k.d = *d;

@@ -243,7 +243,8 @@ PBR_HD void ct_forward_group(const CtStage& S, const CtFlags& F, const V (&araw)
 //   fetch(l)                    : software prefetch hook of the generic kernels: "what was fetched last becomes
 //        current, start loading the grad_out / target of light l" (l == L: rotate only).  gout(l) then reads the
 //        current buffer, which was requested one whole light iteration earlier.
-//   int_sink(l, g_int[3])       : per-light intensity gradient summed over the texels of the group.
+//   int_sink(l, g_int[3])       : per-light intensity gradient summed over the texels of the group (only called when
+//        `want_int`, the last argument, is set).
 //   gc                          : kLightPointCached only, the calling thread's geometry cache.
 // Results: d_albedo/d_normal/d_met [3][N], d_rough[N].
 // ------------------------------------------------------------------------------------------------
@@ -293,7 +294,7 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
                               const LightGeomT<V> (&hoisted)[N], Gout gout, IntSink int_sink, V (&d_albedo)[3][N],
                               V (&d_normal)[3][N], V (&d_rough)[N], V (&d_met)[3][N], Fetch fetch = Fetch(),
                               GeomCache<V> gc = GeomCache<V>(), GeomSink geom_sink = GeomSink(),
-                              SavedOut saved_out = SavedOut()) {
+                              SavedOut saved_out = SavedOut(), bool want_int = true) {
   constexpr bool kGeom = GeomSink::kOn;
   static_assert(!kGeom || kLight == kLightDirectional || kLight == kLightPoint || kLight == kLightPointCached,
                 "geometry gradients: directional, per-texel point lights, or the 6-field geometry cache");
@@ -405,8 +406,10 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
       V gi[3];
       GeomGrad<V> gg;
       shade_light_bwd<kWorkflow, kGeom>(t[i], g[i], S.light[l].inten, f[i], gcol, tg[i], gi, &gg);
+      if (want_int) {   // (uniform over the launch: the intensity gradient's arithmetic is skipped when nobody asked for it)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) gi_sum[c] += lane_sum(gi[c]);
+        for (int c = 0; c < 3; ++c) gi_sum[c] += lane_sum(gi[c]);
+      }
       if (kGeom) {
         V glt[3];
         light_geom_bwd<kLight != kLightDirectional>(g[i], gg, S.light[l].p, x[i], y, S.vx, S.vy, S.vz, glt, g_view[i]);
@@ -414,7 +417,7 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
         for (int c = 0; c < 3; ++c) glt_sum[c] += lane_sum(glt[c]);
       }
     }
-    int_sink(l, gi_sum);
+    if (want_int) int_sink(l, gi_sum);
     if (kGeom) geom_sink.light(l, glt_sum);
   }
   fetch(-1);   // the light loop is over and its registers are free: the caller may start loading whatever comes next

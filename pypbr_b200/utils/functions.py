@@ -72,10 +72,11 @@ def linear_to_srgb(texture: torch.Tensor) -> torch.Tensor:
     return _color_convert(texture, False)
 
 
-def _normal_op(src: torch.Tensor, out: torch.Tensor, op: int, cos_a=0.0, sin_a=0.0, scale=0.0, flip_y=0) -> torch.Tensor:
+def _normal_op(src: torch.Tensor, out: torch.Tensor, op: int, cos_a=0.0, sin_a=0.0, scale=0.0, flip_y=0, aux=None) -> torch.Tensor:
     lib = _cabi.load()
     B = src.shape[0] if src.dim() == 4 else 1
-    d = _cabi.PbrNormalOpDesc(B, src.shape[-2], src.shape[-1], op, cos_a, sin_a, scale, flip_y, _cabi.plane(src), _cabi.plane(out))
+    d = _cabi.PbrNormalOpDesc(B, src.shape[-2], src.shape[-1], op, cos_a, sin_a, scale, flip_y, _cabi.plane(src), _cabi.plane(out),
+                              _cabi.plane(aux))
     with torch.cuda.device(src.device):
         _cabi.check(lib.pbr_normal_op(_cabi.byref(d), _cabi.stream_ptr(src.device)), "pbr_normal_op")
     return out
@@ -128,14 +129,37 @@ def compute_normal_from_height(height_map: torch.Tensor, scale: float = 1.0,
         height_map = height_map.unsqueeze(0)
     if height_map.dim() not in (3, 4) or height_map.shape[-3] != 1:
         raise ValueError(f"height_map must have shape (H, W), (1, H, W) or (B, 1, H, W), got {tuple(height_map.shape)}")
+    flip = 1 if convention == NormalConvention.DIRECTX else 0
     if torch.is_grad_enabled() and height_map.requires_grad:
-        raise RuntimeError("pypbr_b200: compute_normal_from_height has no adjoint kernel; pass height_map.detach()")
-    src = _cabi.rowmajor(height_map.detach())
+        return _NormalFromHeightFn.apply(height_map, float(scale), flip)
+    return _normal_from_height(_cabi.rowmajor(height_map.detach()), float(scale), flip)
+
+
+def _normal_from_height(src: torch.Tensor, scale: float, flip: int) -> torch.Tensor:
     shape = list(src.shape)
     shape[-3] = 3
     out = torch.empty(shape, dtype=torch.float32, device=src.device)
-    return _normal_op(src, out, _cabi.NORMAL_OP_FROM_HEIGHT, scale=float(scale),
-                      flip_y=1 if convention == NormalConvention.DIRECTX else 0)
+    return _normal_op(src, out, _cabi.NORMAL_OP_FROM_HEIGHT, scale=scale, flip_y=flip)
+
+
+class _NormalFromHeightFn(torch.autograd.Function):
+    """compute_normal_from_height with its adjoint (pbr_normal_op FROM_HEIGHT_BWD): the reference's pad / difference /
+    normalise sequence (utils/functions.py:144-175) is differentiable, so a height map can be fitted through its normals."""
+
+    @staticmethod
+    def forward(ctx, height_map, scale: float, flip: int):
+        src = _cabi.rowmajor(height_map.detach())
+        ctx.save_for_backward(src)
+        ctx.args = (scale, flip)
+        return _normal_from_height(src, scale, flip)
+
+    @staticmethod
+    def backward(ctx, g):
+        (src,) = ctx.saved_tensors
+        scale, flip = ctx.args
+        d_h = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+        _normal_op(src, d_h, _cabi.NORMAL_OP_FROM_HEIGHT_BWD, scale=scale, flip_y=flip, aux=_cabi.rowmajor(g))
+        return d_h, None, None
 
 
 def compute_height_from_normal(normal_map: torch.Tensor, scale: float = 1.0,
