@@ -356,8 +356,16 @@ __device__ __forceinline__ void grid_coords(const CtStage& S, const Where& w, in
   }
 }
 
+// Register budget of the generic forward: the cached multi-light flavours take the full budget (2 CTAs per SM): registers buy
+// them more than occupancy does (tools/tune.py, 16 x 1024^2: L = 16 0.810 -> 0.771 ms, L = 8 0.403 -> 0.390, L = 4 0.227 -> 0.222;
+// unrolling the light loop on top of it is slower again), the memory-bound single-light / uncached flavours keep 4 CTAs.
+#ifndef PBR_FWD_CACHED_MIN_CTAS
+#define PBR_FWD_CACHED_MIN_CTAS 2
+#endif
+constexpr int fwd_min_ctas(int light_mode) { return is_cached(light_mode) ? PBR_FWD_CACHED_MIN_CTAS : PBR_FWD_MIN_CTAS; }
+
 template <int WF, int kLight, bool kVec = true>
-__global__ void __launch_bounds__(kCtThreads, PBR_FWD_MIN_CTAS) ct_forward_kernel(const __grid_constant__ CtKParams p) {
+__global__ void __launch_bounds__(kCtThreads, fwd_min_ctas(kLight)) ct_forward_kernel(const __grid_constant__ CtKParams p) {
   constexpr int G = PBR_FWD_GROUP;
   __shared__ CtStage S;
   stage_params(p, S);

@@ -651,7 +651,13 @@ def test_one_launch_fit_step_equals_loss_kernel_plus_adam_kernel(L, wf, normal, 
                     # (5 < L <= 8: the loss kernel caches attenuation and (1-h.v)^5 per light, the fit kernel - whose Adam staging
                     # needs the shared memory - recomputes them from the plane position: a few ulp of the gradient)
                     tol = 5e-6 * a.abs() + 2e-6 * a.abs().mean() + (2e-7 if what == "param" else 0.0)
-                    assert bool((err <= tol).all()), (k, what, float((err / tol).max()))
+                    ok = err <= tol
+                    if what == "param":
+                        # an Adam step is lr-sized whatever the gradient: where the gradient is at noise level (|m| ~ eps) a few
+                        # ulp of it move the step by a visible fraction of lr, so the parameter is compared where it is defined
+                        m1 = oa.state[k][0].abs()
+                        ok = ok | (m1 <= 1e-4 * m1.mean())
+                    assert bool(ok.all()), (k, what, float((err / tol)[~ok].max()))
     finally:
         ct.FORCE_GENERIC = False
     assert losses[-1] < losses[0]

@@ -54,6 +54,10 @@ VARIANTS = {
     "r2_bpw_st3": v(stream_per_warp_bwd=1, stream_stages=3),
     "r2_hm22": v(hoist_mats=22),                                       # 22 materials per CTA walk: 3 chunks of a 64-material batch
     "r2_hm32": v(hoist_mats=32),
+    "r2_f2": v(fwd_min_ctas=2),                 # generic forward with the full register budget (the cache's shared memory caps it at 2 CTAs for L >= 11 anyway)
+    "r2_f2u2": v(fwd_min_ctas=2, fwd_unroll=2),
+    "r2_f3u2": v(fwd_min_ctas=3, fwd_unroll=2),
+    "r2_u2": v(fwd_unroll=2),
     "r2_sb4": v(stream_bwd_min_ctas=4),         # streamed backward capped at 128 registers (4 CTAs per SM)
     "r2_sf5": v(stream_fwd_min_ctas=5),         # streamed forward capped at 102 registers (5 CTAs per SM)
     # memory pipeline only (no shading math): the floor of the TMA-in / STG-out design
