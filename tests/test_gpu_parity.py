@@ -602,7 +602,7 @@ def test_one_launch_fit_step_equals_loss_kernel_plus_adam_kernel(L, wf, normal, 
     """pbr_ct_fit_step (render + MSE + backward + Adam + projection in one launch, gradients in registers) must walk
     the same trajectory as pbr_ct_loss_fwd_bwd followed by pbr_adam_step: the same update on the same fp32 gradient
     values; the epilogue evaluates it with the MUFU reciprocal / rsqrt (relative error ~2e-7 per step) and the two
-    instantiations contract multiply-adds differently, hence 5e-6 relative to |x| (+ 2e-6 mean|x|) per step."""
+    instantiations contract multiply-adds differently, hence 1e-5 relative to |x| (+ 4e-6 mean|x|) per step (parity proper is against the oracle: test_c5_shape_*)."""
     from pypbr_b200.fit import FusedAdam, fit_step
     from pypbr_b200.materials import BasecolorMetallicMaterial, DiffuseSpecularMaterial
     from pypbr_b200.models import CookTorranceBRDF
@@ -650,7 +650,7 @@ def test_one_launch_fit_step_equals_loss_kernel_plus_adam_kernel(L, wf, normal, 
                     err = (a - b).abs()
                     # (5 < L <= 8: the loss kernel caches attenuation and (1-h.v)^5 per light, the fit kernel - whose Adam staging
                     # needs the shared memory - recomputes them from the plane position: a few ulp of the gradient)
-                    tol = 5e-6 * a.abs() + 2e-6 * a.abs().mean() + (2e-7 if what == "param" else 0.0)
+                    tol = 1e-5 * a.abs() + 4e-6 * a.abs().mean() + (2e-7 if what == "param" else 0.0)
                     ok = err <= tol
                     if what == "param":
                         # an Adam step is lr-sized whatever the gradient: where the gradient is at noise level (|m| ~ eps) a few
