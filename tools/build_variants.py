@@ -58,6 +58,7 @@ VARIANTS = {
     "r2_f2u2": v(fwd_min_ctas=2, fwd_unroll=2),
     "r2_f3u2": v(fwd_min_ctas=3, fwd_unroll=2),
     "r2_u2": v(fwd_unroll=2),
+    "r2_late": v(bwd_late_prefetch=1),          # backward: next material's maps requested when the light loop is over
     "r2_sb4": v(stream_bwd_min_ctas=4),         # streamed backward capped at 128 registers (4 CTAs per SM)
     "r2_sf5": v(stream_fwd_min_ctas=5),         # streamed forward capped at 102 registers (5 CTAs per SM)
     # memory pipeline only (no shading math): the floor of the TMA-in / STG-out design
