@@ -182,6 +182,8 @@ struct CtKParams {
   // writing the gradients.  Moments in the order albedo, normal, roughness, metspec.
   int adam_on, adam_project;
   int adam_smem_off;     // byte offset of the Adam staging area in the dynamic shared memory (after the geometry cache)
+  int part_on;           // shared-parameter gradients are accumulated in per-thread shared-memory slots (see ct_backward_kernel)
+  int part_smem_off;     // ... at this byte offset of the dynamic shared memory
   AdamCoef adam;
   PbrPlane adam_m[4], adam_v[4];
   // staging sources
@@ -496,12 +498,15 @@ struct CtaSavedOut {
   }
 };
 
-// Sink of the geometry gradients (kGeom kernels): warp shuffle -> shared atomics, flushed once per CTA.
+// Sink of the geometry gradients (kGeom kernels).  Per light: into the calling thread's own shared-memory slots (`part`, see
+// ct_backward_kernel) when the launch has them, else warp shuffle -> shared atomics; the view gradient (once per material and
+// texel pair) always takes the shuffle.  Flushed once per CTA.
 struct CtaGeomSink {
   static constexpr bool kOn = true;
   float* s_geo;   // [L][3] lights, then [3] view
   int L, tid;
   float live;
+  float* part;    // this thread's column of the partial-sum slots, or nullptr
   __device__ __forceinline__ void add(int slot, const float (&g)[3]) const {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -509,7 +514,14 @@ struct CtaGeomSink {
       if ((tid & 31) == 0) atomicAdd(&s_geo[3 * slot + c], sum);
     }
   }
-  __device__ __forceinline__ void light(int l, const float (&g)[3]) const { add(l, g); }
+  __device__ __forceinline__ void light(int l, const float (&g)[3]) const {
+    if (part) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) part[(l * 6 + 3 + c) * kCtThreads] += g[c] * live;
+    } else {
+      add(l, g);
+    }
+  }
   __device__ __forceinline__ void view(const float (&g)[3]) const { add(L, g); }
 };
 
@@ -531,6 +543,16 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
   }
   if (kGeom) {
     for (int i = tid; i < (p.flags.L + 1) * 3; i += kCtThreads) s_geo[i] = 0.0f;
+  }
+  // Shared-parameter gradients (d_intensity; kGeom: + d_lights) are sums over every texel, light by light.  A warp shuffle
+  // reduction + shared atomic per light and value - 30 SHFL per texel-pair-light with kGeom - made the fit with unknown
+  // lighting 2.4x slower than the plain loss kernel (24.9 vs 10.4 ms on C5).  Each thread therefore adds into its OWN
+  // shared-memory slots, [value][thread] (one LDS + FADD + STS, no synchronisation), over all the lights and all the
+  // materials it walks over, and the CTA reduces the slots once at the end.  K values per light: 3 (intensity) or 6 (kGeom).
+  constexpr int K = kGeom ? 6 : 3;
+  float* const s_part = p.part_on ? reinterpret_cast<float*>(s_dyn + p.part_smem_off) + tid : nullptr;
+  if (s_part) {
+    for (int i = 0; i < p.flags.L * K; ++i) s_part[i * kCtThreads] = 0.0f;
   }
   stage_params(p, S);  // ends with __syncthreads()
   const Where w = locate_ct<kVec>(p);
@@ -701,10 +723,15 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       };
       auto int_sink = [&](int l, const float(&gi)[3]) {
         if (int_grad) {
+          if (s_part) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float sum = warp_sum(gi[c] * live);
-            if ((tid & 31) == 0) atomicAdd(&s_int[3 * l + c], sum);
+            for (int c = 0; c < 3; ++c) s_part[(l * K + c) * kCtThreads] += gi[c] * live;
+          } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float sum = warp_sum(gi[c] * live);
+              if ((tid & 31) == 0) atomicAdd(&s_int[3 * l + c], sum);
+            }
           }
         }
       };
@@ -713,7 +740,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       gcs.base += s * gc.stride;
       if constexpr (kGeom) {
         ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs,
-                                            CtaGeomSink{s_geo, p.flags.L, tid, live}, CtaSavedOut{ring + 3 * (kCtThreads * NT), have_fout}, int_grad);
+                                            CtaGeomSink{s_geo, p.flags.L, tid, live, s_part}, CtaSavedOut{ring + 3 * (kCtThreads * NT), have_fout}, int_grad);
       } else {
         ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs,
                                             NoGeomSink(), CtaSavedOut{ring + 3 * (kCtThreads * NT), have_fout}, int_grad);
@@ -808,6 +835,26 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
     loss_local += lane_sum(loss_v);
     float sum = warp_sum(loss_local * live);
     if ((tid & 31) == 0) s_loss[tid >> 5] = sum;
+  }
+  if (p.part_on) {
+    // the per-thread slots -> the CTA's sums: warp w reduces values w, w + 4, ... (128 slots each: 4 per lane, then a shuffle)
+    __syncthreads();
+    const float* base = reinterpret_cast<const float*>(s_dyn + p.part_smem_off);
+    const int lane = tid & 31;
+    for (int v = tid >> 5; v < p.flags.L * K; v += kCtThreads / 32) {
+      float sum = 0.0f;
+#pragma unroll
+      for (int j = 0; j < kCtThreads / 32; ++j) sum += base[v * kCtThreads + lane + 32 * j];
+      sum = warp_sum(sum);
+      if (lane == 0) {
+        const int l = v / K, j = v - l * K;
+        if (j < 3) {
+          if (int_grad) s_int[3 * l + j] += sum;          // one writer per value
+        } else if (kGeom) {
+          s_geo[3 * l + (j - 3)] += sum;
+        }
+      }
+    }
   }
   if (is_loss || int_grad || kGeom) __syncthreads();
   if (kGeom) {
@@ -1181,6 +1228,8 @@ static void ct_launch_shape(CtKParams& k, dim3& grid, dim3& block, bool backward
   grid.z = (k.B + k.mats_per_cta - 1) / k.mats_per_cta;
 }
 
+// most dynamic shared memory a generic kernel is ever launched with: geometry cache + Adam staging (or the partial-sum slots)
+constexpr size_t kMaxDynSmem = (size_t)PBR_GC_MAX_BYTES + 30 * kCtThreads * kCtTexels * 4;
 // launch with `smem` bytes of dynamic shared memory (opt-in above 48 KB, once per kernel instantiation and device)
 template <void (*Kern)(CtKParams)>
 static void launch_dyn(const CtKParams& k, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
@@ -1189,7 +1238,7 @@ static void launch_dyn(const CtKParams& k, dim3 grid, dim3 block, size_t smem, c
   cudaGetDevice(&dev);
   const uint64_t bit = 1ull << (dev & 63);
   if (!(configured.load(std::memory_order_acquire) & bit)) {   // static + dynamic may exceed 48 KB before dynamic alone does
-    cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PBR_GC_MAX_BYTES + 30 * kCtThreads * kCtTexels * 4);
+    cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem);
     configured.fetch_or(bit, std::memory_order_release);
   }
   Kern<<<grid, block, smem, st>>>(k);
@@ -1227,7 +1276,17 @@ static void launch_bwd(const CtKParams& k_in, dim3 grid, dim3 block, cudaStream_
   const int lm = light_mode(k, true);
   const size_t cache = is_cached(lm) ? geom_cache_bytes(k.flags.L, lm) : 0;
   k.adam_smem_off = (int)cache;
-  const size_t smem = cache + (k.adam_on ? kAdamSmemBytes : 0);
+  size_t smem = cache + (k.adam_on ? kAdamSmemBytes : 0);
+  // per-thread slots of the shared-parameter gradients, when they fit next to the cache (else: warp-shuffle reduction per light)
+  k.part_on = 0;
+  if (k.d_intensity || k.d_lights || k.d_view) {
+    const size_t part = (size_t)k.flags.L * ((k.d_lights || k.d_view) ? 6 : 3) * kCtThreads * sizeof(float);
+    if (part <= 48 * 1024 && smem + part <= kMaxDynSmem) {
+      k.part_on = 1;
+      k.part_smem_off = (int)smem;
+      smem += part;
+    }
+  }
   if (k.d_lights || k.d_view) {   // geometry gradients: the uncached per-texel light modes
     if (k.vec_fast) {
       if (lm == kLightPointCached) launch_dyn<ct_backward_kernel<WF, kLightPointCached, true>>(k, grid, block, smem, st);

@@ -650,7 +650,9 @@ def test_one_launch_fit_step_equals_loss_kernel_plus_adam_kernel(L, wf, normal, 
                     err = (a - b).abs()
                     # (5 < L <= 8: the loss kernel caches attenuation and (1-h.v)^5 per light, the fit kernel - whose Adam staging
                     # needs the shared memory - recomputes them from the plane position: a few ulp of the gradient)
-                    tol = 1e-5 * a.abs() + 4e-6 * a.abs().mean() + (2e-7 if what == "param" else 0.0)
+                    # (a gradient is a sum over the lights with cancellation: an ulp of one light's attenuation shows up
+                    # relative to the mean magnitude, not to the element)
+                    tol = 1e-5 * a.abs() + 2e-5 * a.abs().mean() + (2e-7 if what == "param" else 0.0)
                     ok = err <= tol
                     if what == "param":
                         # an Adam step is lr-sized whatever the gradient: where the gradient is at noise level (|m| ~ eps) a few
