@@ -585,6 +585,8 @@ def _normal_ingest_cuda(t: torch.Tensor, channels: int, out: Optional[torch.Tens
         d.cond_min = cond_min.data_ptr()
     with torch.cuda.device(t.device):
         _cabi.check(lib.pbr_normal_ingest(_cabi.byref(d), _cabi.stream_ptr(t.device)), "pbr_normal_ingest")
+    if out is t:
+        _cabi.touch(t)   # written in place through its raw pointer
     return out
 
 
