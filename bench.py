@@ -779,6 +779,23 @@ def measure_e2e(args, ctx, cfg, tgt_brdf_inputs):
     pipe = _Pipe(dev)
     unit = [0]
 
+    # the ceiling of this leg on this host at this N: the same pinned buffers copied to the device with nothing else going on,
+    # every rank at once (tools/h2d_scaling.py: 55 / 111 / 115 / 187 GB/s in total at 1 / 2 / 4 / 8 ranks on the 8-GPU box)
+    ceil_dst = {k: torch.empty_like(v, device=dev) for k, v in host8.items()}
+
+    def copy_all():
+        for k in host8:
+            ceil_dst[k].copy_(host8[k], non_blocking=True)
+
+    copy_all()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        copy_all()
+    torch.cuda.synchronize()
+    h2d_ceiling = 4 * h2d8 / ctx.max_over_ranks(time.perf_counter() - t0) / 1e9
+    del ceil_dst
+
     def chunk_material(slot, requires_grad):
         m = BasecolorMetallicMaterial(albedo_is_srgb=True, device=dev)
         leaves = []
@@ -822,7 +839,10 @@ def measure_e2e(args, ctx, cfg, tgt_brdf_inputs):
                "path": "pinned host uint8 (B,H,W,C) textures -> H2D in chunks of 8 materials (copy stream, double-buffered) -> pbr_ingest_image x4 -> "
                        "CookTorranceBRDF.__call__ (pbr_ct_forward) -> torch.autograd.grad (pbr_ct_backward; map gradients stay in HBM for the optimiser) -> "
                        "D2H of d(light_intensity) (12 bytes)",
-               "h2d_gbs": h2d8 / (dt / n_steps) / 1e9, "numa": ctx.numa}
+               "h2d_gbs": h2d8 / (dt / n_steps) / 1e9, "h2d_ceiling_gbs": h2d_ceiling,
+               "frac_of_h2d_ceiling": h2d8 / (dt / n_steps) / 1e9 / h2d_ceiling,
+               "bound": "host->device copy rate of this host at this many ranks (h2d_ceiling_gbs: the same buffers copied with no kernels "
+                        "running, all ranks at once, measured in this run)", "numa": ctx.numa}
 
     def step_fit_u8(s):
         for c in range(n_chunks):
