@@ -60,20 +60,28 @@ constexpr int kTileFloats = kStreamThreads * kST;   // floats of one plane in on
 // PBR_STREAM_PER_WARP: every warp runs its OWN copy pipeline over its own 32 x kST texels of a tile row (plane stride
 // inside a stage = one warp segment) instead of warp 0 feeding the whole CTA: a warp refills a stage right after its own
 // last read of it, without waiting for the other warps or for its own arithmetic.
-// Measured (C2 shape, tools/tune.py): forward 0.499 -> 0.474 ms (95 % of the HBM copy peak); the backward, whose refill
-// point sits between the two pairs it shades one after the other, is 1.5 % slower that way (0.944 -> 0.959 ms) and keeps
-// the CTA-level pipeline.  Deeper pipelines (3, 4 stages) are slower in both.
+// Measured (C2 shape, tools/tune.py): forward 0.499 -> 0.474 ms (95 % of the HBM copy peak).  The backward used to be
+// 1.5 % slower that way (0.944 -> 0.959 ms): the per-warp issue of 11 small copies per tile cost what the decoupling gave.
+// With the kFast flavour (below) the balance flips - CTA-level 0.852 ms, per-warp 0.807 ms at 64 x 1024^2
+// (profiles/r2_tune_c2_kfast_variants.json) - so both kernels run per-warp pipelines.  Deeper pipelines (3, 4 stages) are
+// slower in both.
 #ifndef PBR_STREAM_PER_WARP_FWD
 #define PBR_STREAM_PER_WARP_FWD 1
 #endif
 #ifndef PBR_STREAM_PER_WARP_BWD
-#define PBR_STREAM_PER_WARP_BWD 0
+#define PBR_STREAM_PER_WARP_BWD 1
 #endif
 #ifndef PBR_STREAM_BWD_LATE_REFILL
 #define PBR_STREAM_BWD_LATE_REFILL 0   // per-warp backward: refill after the whole tile instead of after the last read
 #endif
 constexpr bool kPerWarpFwd = PBR_STREAM_PER_WARP_FWD != 0, kPerWarpBwd = PBR_STREAM_PER_WARP_BWD != 0;
 constexpr bool kLateRefill = PBR_STREAM_BWD_LATE_REFILL != 0;
+// CTA-level backward: the warp that reads a stage LAST refills it at once (a shared-memory counter elects it) instead of
+// warp 0 doing so after it has shaded its own second pair and waited for the other warps on the `empty` barrier.
+#ifndef PBR_STREAM_BWD_LAST_REFILL
+#define PBR_STREAM_BWD_LAST_REFILL 0
+#endif
+constexpr bool kLastRefill = PBR_STREAM_BWD_LAST_REFILL != 0 && !kPerWarpBwd;
 constexpr int kWarpSeg = 32 * kST;                                  // floats of one plane a warp owns per tile row
 constexpr int kMaxPipes = kStreamThreads / 32;                      // independent copy pipelines per CTA (per-warp mode)
 PBR_HDC int plane_stride(bool per_warp) { return per_warp ? kWarpSeg : kStreamThreads * kST; }   // floats between two planes of a stage
@@ -93,6 +101,7 @@ struct StreamSrc {
 struct StreamShared {
   uint64_t full[kStages * kMaxPipes];   // producer -> consumers: the copies of the stage have landed (transaction bytes)
   uint64_t empty[kStages];   // consumers -> producer: one arrival per warp after its last read of the stage
+  int readers[kStages];      // kLastRefill: warps that have read the stage's current tile
   StreamSrc src[kMaxSrcPlanes];
   int n_src;
 };
@@ -131,8 +140,7 @@ __device__ __forceinline__ void stream_build_table(const CtKParams& p, int row0,
 
 // warp 0: enqueue the copies of material `b` into `stage` (floats) and arm its barrier
 __device__ __forceinline__ void stream_issue(const StreamShared& sh, uint64_t* bar, float* stage, int b, int rows_valid,
-                                             int seg_bytes, int row_floats, uint64_t policy) {
-  const int lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
+                                             int seg_bytes, int row_floats, uint64_t policy, int lane) {
   const int items = sh.n_src * rows_valid;
   if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(items * seg_bytes));
   __syncwarp();
@@ -210,6 +218,43 @@ __device__ __forceinline__ StreamWhere stream_locate(int H, int W) {
   }
   return w;
 }
+// kFast flavour of the streamed kernels (round 2).  The host picks it when the launch is the plain case: blockDim = (kStreamThreads, 1),
+// every tile full (W % (kStreamThreads * kST) == 0), a normal map, and - in the backward - all four gradient planes requested.
+// Then the tile geometry is compile-time (immediate LDS / STG offsets), no slot or output is ever inactive, and the loop
+// carries no null checks: ncu had ~215 of the backward's 1172 instructions per tile and warp on index rematerialisation
+// (S2R, LDC, IMAD), predicates on the output pointers and 64-bit address rebuilds; a lean loop needs ~65.
+// Measured at 64 x 1024^2 (bare C ABI): backward 0.923 -> 0.852 ms (586 M -> 519 M warp-instructions), with per-warp
+// pipelines 0.807 ms = 96 % of the measured copy peak (floor with the math compiled out: 0.775 ms); forward
+// 0.461 -> 0.446 ms = the copy peak.
+#ifndef PBR_STREAM_FAST
+#define PBR_STREAM_FAST 1
+#endif
+constexpr bool kStreamFast = PBR_STREAM_FAST != 0;
+template <bool kPerWarp>
+__device__ __forceinline__ StreamWhere stream_locate_fast() {
+  StreamWhere w;
+  w.row_floats = kTileFloats;
+  w.row0 = blockIdx.y;
+  w.col0 = blockIdx.x * kTileFloats;
+  w.row = w.row0;
+  w.rows_valid = 1;
+  w.row_ok = true;
+  if (kPerWarp) {
+    const int lane = threadIdx.x & 31;
+    w.wcol = (threadIdx.x >> 5) * kWarpSeg;
+    w.slot_stride = 32 * kLanes;
+    w.col = w.col0 + w.wcol + lane * kLanes;
+    w.toff = lane * kLanes;
+    w.seg_bytes = kWarpSeg * 4;
+  } else {
+    w.wcol = 0;
+    w.slot_stride = kStreamThreads * kLanes;
+    w.col = w.col0 + threadIdx.x * kLanes;
+    w.toff = threadIdx.x * kLanes;
+    w.seg_bytes = kTileFloats * 4;
+  }
+  return w;
+}
 // W % 4 == 0 (and kLanes <= 2): a slot's texels are all inside or all outside the image
 __device__ __forceinline__ bool slot_active(const StreamWhere& w, int j, int W) { return w.row_ok && w.col + j * w.slot_stride < W; }
 
@@ -235,7 +280,7 @@ __device__ __forceinline__ void stream_coords(const CtStage& S, const StreamWher
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int WF, int kLight>
+template <int WF, int kLight, bool kFast = false>
 __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_FWD_MIN_CTAS) ct_forward_stream(const __grid_constant__ CtKParams p) {
   using SL = Slots<WF, false>;
   constexpr int G = kSSlots;   // all of the thread's pairs are shaded together
@@ -244,8 +289,9 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_FWD_MIN_CTAS) ct_fo
   extern __shared__ __align__(128) float stream_smem[];
   __shared__ CtStage S;
   __shared__ StreamShared sh;
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const StreamWhere w = stream_locate<kPerWarp>(p.H, p.W);
+  const int tid = kFast ? threadIdx.x : threadIdx.y * blockDim.x + threadIdx.x;
+  const StreamWhere w = kFast ? stream_locate_fast<kPerWarp>() : stream_locate<kPerWarp>(p.H, p.W);
+  const int row_in_tile = kFast ? 0 : threadIdx.y;
   if (tid == 0) {
     stream_build_table<WF, false>(p, w.row0, w.col0, sh);
 #pragma unroll
@@ -258,7 +304,7 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_FWD_MIN_CTAS) ct_fo
 
   const int b0 = blockIdx.z * p.mats_per_cta;
   const int ntiles = min(b0 + p.mats_per_cta, p.B) - b0;
-  const int stage_floats = (p.normal.ptr ? SL::count : SL::count_no_normal) * kTileFloats;
+  const int stage_floats = ((kFast || p.normal.ptr) ? SL::count : SL::count_no_normal) * kTileFloats;
   uint64_t policy = 0;
   // per-warp pipelines: this warp's barriers and stage buffers (planes x kWarpSeg floats per stage)
   const int pipe = kPerWarp ? (tid >> 5) : 0;
@@ -269,22 +315,22 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_FWD_MIN_CTAS) ct_fo
     policy = l2_evict_first_policy();
     if (w.seg_bytes > 0)
       for (int k = 0; k < kStages && k < ntiles; ++k)
-        warp_issue(sh, &full[k], my_stages + k * my_stage_floats, b0 + k, threadIdx.y, w.wcol, w.seg_bytes, policy);
+        warp_issue(sh, &full[k], my_stages + k * my_stage_floats, b0 + k, row_in_tile, w.wcol, w.seg_bytes, policy);
   } else if (tid < 32) {
     policy = l2_evict_first_policy();
     for (int k = 0; k < kStages && k < ntiles; ++k)
-      stream_issue(sh, &sh.full[k], stream_smem + k * stage_floats, b0 + k, w.rows_valid, w.seg_bytes, w.row_floats, policy);
+      stream_issue(sh, &sh.full[k], stream_smem + k * stage_floats, b0 + k, w.rows_valid, w.seg_bytes, w.row_floats, policy, tid);
   }
 
   V x[kSSlots];
   float y;
   LightGeomT<V> hg[kSSlots];
   stream_coords<kLight>(S, w, p.W, x, y, hg);
-  const bool has_normal = p.normal.ptr != nullptr;
+  const bool has_normal = kFast || p.normal.ptr != nullptr;
   bool act[kSSlots];
   bool any = false;
 #pragma unroll
-  for (int j = 0; j < kSSlots; ++j) { act[j] = slot_active(w, j, p.W); any = any || act[j]; }
+  for (int j = 0; j < kSSlots; ++j) { act[j] = kFast || slot_active(w, j, p.W); any = any || act[j]; }
   // output pointer of material b0 at slot 0; advanced by one batch stride per tile (strides sit in the
   // __grid_constant__ parameter block, i.e. the constant bank)
   float* o = p.out.ptr + ((int64_t)b0 * p.out.sb + (int64_t)w.row * p.out.sh + w.col);
@@ -311,7 +357,7 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_FWD_MIN_CTAS) ct_fo
     if (kPerWarp) {
       if (w.seg_bytes > 0 && k + kStages < ntiles) {
         fence_proxy_async();
-        warp_issue(sh, &full[s], my_stages + s * my_stage_floats, b0 + k + kStages, threadIdx.y, w.wcol, w.seg_bytes, policy);
+        warp_issue(sh, &full[s], my_stages + s * my_stage_floats, b0 + k + kStages, row_in_tile, w.wcol, w.seg_bytes, policy);
       }
     } else if ((tid & 31) == 0) {
       mbar_arrive(&sh.empty[s]);
@@ -345,7 +391,7 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_FWD_MIN_CTAS) ct_fo
     if (!kPerWarp && tid < 32 && k + kStages < ntiles) {
       mbar_wait(&sh.empty[s], (k / kStages) & 1);
       stream_issue(sh, &sh.full[s], stream_smem + s * stage_floats, b0 + k + kStages, w.rows_valid, w.seg_bytes,
-                   w.row_floats, policy);
+                   w.row_floats, policy, tid);
     }
   }
 }
@@ -353,7 +399,7 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_FWD_MIN_CTAS) ct_fo
 // ------------------------------------------------------------------------------------------------
 // backward / fused loss
 // ------------------------------------------------------------------------------------------------
-template <int WF, int kLight, int kMode>
+template <int WF, int kLight, int kMode, bool kFast = false>
 __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_backward_stream(const __grid_constant__ CtKParams p) {
   using SL = Slots<WF, true>;
   constexpr bool kPerWarp = kPerWarpBwd;
@@ -364,12 +410,12 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_ba
   __shared__ CtStage S;
   __shared__ StreamShared sh;
   __shared__ float s_red[kStreamThreads / 32][4];
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const StreamWhere w = stream_locate<kPerWarp>(p.H, p.W);
+  const int tid = kFast ? threadIdx.x : threadIdx.y * blockDim.x + threadIdx.x;
+  const StreamWhere w = kFast ? stream_locate_fast<kPerWarp>() : stream_locate<kPerWarp>(p.H, p.W);
   if (tid == 0) {
     stream_build_table<WF, true>(p, w.row0, w.col0, sh);
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) mbar_init(&sh.empty[s], kStreamThreads / 32);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&sh.empty[s], kStreamThreads / 32); sh.readers[s] = 0; }
 #pragma unroll
     for (int s = 0; s < kStages * kPipes; ++s) mbar_init(&sh.full[s], 1);
     mbar_init_fence();
@@ -378,34 +424,36 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_ba
 
   const int b0 = blockIdx.z * p.mats_per_cta;
   const int ntiles = min(b0 + p.mats_per_cta, p.B) - b0;
-  const int stage_floats = (p.normal.ptr ? SL::count : SL::count_no_normal) * kTileFloats;
+  const int stage_floats = ((kFast || p.normal.ptr) ? SL::count : SL::count_no_normal) * kTileFloats;
   uint64_t policy = 0;
+  if (kLastRefill) policy = l2_evict_first_policy();
   // per-warp pipelines: this warp's barriers and stage buffers (planes x kWarpSeg floats per stage)
   const int pipe = kPerWarp ? (tid >> 5) : 0;
   uint64_t* const full = sh.full + pipe * kStages;
   float* const my_stages = stream_smem + (kPerWarp ? pipe * kStages * (stage_floats / (kTileFloats / kWarpSeg)) : 0);
   const int my_stage_floats = kPerWarp ? stage_floats / (kTileFloats / kWarpSeg) : stage_floats;
+  const int row_in_tile = kFast ? 0 : threadIdx.y;
   if (kPerWarp) {
     policy = l2_evict_first_policy();
     if (w.seg_bytes > 0)
       for (int k = 0; k < kStages && k < ntiles; ++k)
-        warp_issue(sh, &full[k], my_stages + k * my_stage_floats, b0 + k, threadIdx.y, w.wcol, w.seg_bytes, policy);
+        warp_issue(sh, &full[k], my_stages + k * my_stage_floats, b0 + k, row_in_tile, w.wcol, w.seg_bytes, policy);
   } else if (tid < 32) {
     policy = l2_evict_first_policy();
     for (int k = 0; k < kStages && k < ntiles; ++k)
-      stream_issue(sh, &sh.full[k], stream_smem + k * stage_floats, b0 + k, w.rows_valid, w.seg_bytes, w.row_floats, policy);
+      stream_issue(sh, &sh.full[k], stream_smem + k * stage_floats, b0 + k, w.rows_valid, w.seg_bytes, w.row_floats, policy, tid);
   }
 
   V x[kSSlots];
   float y;
   LightGeomT<V> hg[kSSlots];
   stream_coords<kLight>(S, w, p.W, x, y, hg);
-  const bool has_normal = p.normal.ptr != nullptr;
+  const bool has_normal = kFast || p.normal.ptr != nullptr;
   // gradient pointers of material b0 at slot 0; advanced by one batch stride per tile
-  float* o_a = p.d_albedo.ptr ? p.d_albedo.ptr + ((int64_t)b0 * p.d_albedo.sb + (int64_t)w.row * p.d_albedo.sh + w.col) : nullptr;
-  float* o_n = (has_normal && p.d_normal.ptr) ? p.d_normal.ptr + ((int64_t)b0 * p.d_normal.sb + (int64_t)w.row * p.d_normal.sh + w.col) : nullptr;
-  float* o_r = p.d_roughness.ptr ? p.d_roughness.ptr + ((int64_t)b0 * p.d_roughness.sb + (int64_t)w.row * p.d_roughness.sh + w.col) : nullptr;
-  float* o_m = p.d_metspec.ptr ? p.d_metspec.ptr + ((int64_t)b0 * p.d_metspec.sb + (int64_t)w.row * p.d_metspec.sh + w.col) : nullptr;
+  float* o_a = (kFast || p.d_albedo.ptr) ? p.d_albedo.ptr + ((int64_t)b0 * p.d_albedo.sb + (int64_t)w.row * p.d_albedo.sh + w.col) : nullptr;
+  float* o_n = (kFast || (has_normal && p.d_normal.ptr)) ? p.d_normal.ptr + ((int64_t)b0 * p.d_normal.sb + (int64_t)w.row * p.d_normal.sh + w.col) : nullptr;
+  float* o_r = (kFast || p.d_roughness.ptr) ? p.d_roughness.ptr + ((int64_t)b0 * p.d_roughness.sb + (int64_t)w.row * p.d_roughness.sh + w.col) : nullptr;
+  float* o_m = (kFast || p.d_metspec.ptr) ? p.d_metspec.ptr + ((int64_t)b0 * p.d_metspec.sb + (int64_t)w.row * p.d_metspec.sh + w.col) : nullptr;
   V loss_pair = splat<V>(0.0f);
   float gi_local[3] = {0.0f, 0.0f, 0.0f};
 
@@ -433,13 +481,28 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_ba
         if (kPerWarp) {
           if (!kLateRefill && w.seg_bytes > 0 && k + kStages < ntiles) {
             fence_proxy_async();
-            warp_issue(sh, &full[s], my_stages + s * my_stage_floats, b0 + k + kStages, threadIdx.y, w.wcol, w.seg_bytes, policy);
+            warp_issue(sh, &full[s], my_stages + s * my_stage_floats, b0 + k + kStages, row_in_tile, w.wcol, w.seg_bytes, policy);
+          }
+        } else if (kLastRefill) {
+          int last = 0;
+          if ((tid & 31) == 0) {
+            __threadfence_block();
+            last = atomicAdd(&sh.readers[s], 1) == kStreamThreads / 32 - 1;
+          }
+          last = __shfl_sync(0xffffffffu, last, 0);
+          if (last) {   // warp-uniform: every warp has read the stage
+            if ((tid & 31) == 0) sh.readers[s] = 0;
+            if (k + kStages < ntiles) {
+              fence_proxy_async();
+              stream_issue(sh, &sh.full[s], stream_smem + s * stage_floats, b0 + k + kStages, w.rows_valid, w.seg_bytes,
+                           w.row_floats, policy, tid & 31);
+            }
           }
         } else if ((tid & 31) == 0) {
           mbar_arrive(&sh.empty[s]);
         }
       }
-      if (slot_active(w, j, p.W)) {
+      if (kFast || slot_active(w, j, p.W)) {
         const V xs[1] = {x[j]};
         const LightGeomT<V> hgs[1] = {hg[j]};
         auto gout = [&](int, const V(&outv)[3][1], V(&g)[3][1]) {
@@ -471,16 +534,16 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_ba
                                             NoGeomSink(), NoSavedOut(), kIntGrad);
 #endif
         const int jo = j * w.slot_stride;
-        if (o_a) {
+        if (kFast || o_a) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) stg_v(o_a + c * p.d_albedo.sc + jo, da[c][0]);
         }
-        if (o_n) {
+        if (kFast || o_n) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) stg_v(o_n + c * p.d_normal.sc + jo, dn[c][0]);
         }
-        if (o_r) stg_v(o_r + jo, dr[0]);
-        if (o_m) {
+        if (kFast || o_r) stg_v(o_r + jo, dr[0]);
+        if (kFast || o_m) {
 #pragma unroll
           for (int c = 0; c < SL::mc; ++c) stg_v(o_m + c * p.d_metspec.sc + jo, dm[c][0]);
         }
@@ -489,17 +552,17 @@ __global__ void __launch_bounds__(kStreamThreads, PBR_STREAM_BWD_MIN_CTAS) ct_ba
     if (kPerWarp && kLateRefill && w.seg_bytes > 0 && k + kStages < ntiles) {
       __syncwarp();
       fence_proxy_async();
-      warp_issue(sh, &full[s], my_stages + s * my_stage_floats, b0 + k + kStages, threadIdx.y, w.wcol, w.seg_bytes, policy);
+      warp_issue(sh, &full[s], my_stages + s * my_stage_floats, b0 + k + kStages, row_in_tile, w.wcol, w.seg_bytes, policy);
     }
-    if (o_a) o_a += p.d_albedo.sb;
-    if (o_n) o_n += p.d_normal.sb;
-    if (o_r) o_r += p.d_roughness.sb;
-    if (o_m) o_m += p.d_metspec.sb;
+    if (kFast || o_a) o_a += p.d_albedo.sb;
+    if (kFast || o_n) o_n += p.d_normal.sb;
+    if (kFast || o_r) o_r += p.d_roughness.sb;
+    if (kFast || o_m) o_m += p.d_metspec.sb;
     // producer: by the time warp 0 has shaded tile k every warp has long since read stage s
-    if (!kPerWarp && tid < 32 && k + kStages < ntiles) {
+    if (!kPerWarp && !kLastRefill && tid < 32 && k + kStages < ntiles) {
       mbar_wait(&sh.empty[s], (k / kStages) & 1);
       stream_issue(sh, &sh.full[s], stream_smem + s * stage_floats, b0 + k + kStages, w.rows_valid, w.seg_bytes,
-                   w.row_floats, policy);
+                   w.row_floats, policy, tid);
     }
   }
 

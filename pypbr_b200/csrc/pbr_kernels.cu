@@ -1371,6 +1371,12 @@ static void stream_launch(const CtKParams& k, dim3 grid, dim3 block, int planes,
 template <int WF>
 static void launch_fwd_stream(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t st) {
   const int planes = k.normal.ptr ? Slots<WF, false>::count : Slots<WF, false>::count_no_normal;
+  const bool fast = kStreamFast && block.x == (unsigned)kStreamThreads && block.y == 1 && (k.W % kTileFloats) == 0 && k.normal.ptr;
+  if (fast) {
+    if (k.flags.point) stream_launch<ct_forward_stream<WF, kLightPointHoisted, true>>(k, grid, block, planes, st);
+    else stream_launch<ct_forward_stream<WF, kLightDirectional, true>>(k, grid, block, planes, st);
+    return;
+  }
   if (k.flags.point) stream_launch<ct_forward_stream<WF, kLightPointHoisted>>(k, grid, block, planes, st);
   else stream_launch<ct_forward_stream<WF, kLightDirectional>>(k, grid, block, planes, st);
 }
@@ -1378,6 +1384,14 @@ static void launch_fwd_stream(const CtKParams& k, dim3 grid, dim3 block, cudaStr
 template <int WF, int kMode>
 static void launch_bwd_stream_m(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t st) {
   const int planes = k.normal.ptr ? Slots<WF, true>::count : Slots<WF, true>::count_no_normal;
+  // the plain case (full tiles of one row, a normal map, every gradient requested) runs the kFast flavour (pbr_ct_stream.cuh)
+  const bool fast = kStreamFast && block.x == (unsigned)kStreamThreads && block.y == 1 && (k.W % kTileFloats) == 0 && k.normal.ptr &&
+                    k.d_albedo.ptr && k.d_normal.ptr && k.d_roughness.ptr && k.d_metspec.ptr;
+  if (fast) {
+    if (k.flags.point) stream_launch<ct_backward_stream<WF, kLightPointHoisted, kMode, true>>(k, grid, block, planes, st);
+    else stream_launch<ct_backward_stream<WF, kLightDirectional, kMode, true>>(k, grid, block, planes, st);
+    return;
+  }
   if (k.flags.point) stream_launch<ct_backward_stream<WF, kLightPointHoisted, kMode>>(k, grid, block, planes, st);
   else stream_launch<ct_backward_stream<WF, kLightDirectional, kMode>>(k, grid, block, planes, st);
 }

@@ -13,11 +13,14 @@
 #ifndef PBR_P1_UNROLL
 #define PBR_P1_UNROLL 2
 #endif
+#ifndef PBR_BWD_UNROLL
+#define PBR_BWD_UNROLL 1   // main light loop of the backward
+#endif
 #ifndef PBR_BOUNDARY_RECOMPUTE
 #define PBR_BOUNDARY_RECOMPUTE 1   // one-pass accumulate backward: texels whose saved output sits at the clamp's upper end recompute the sum
 #endif
 namespace pbr {
-constexpr int kFwdUnroll = PBR_FWD_UNROLL, kP1Unroll = PBR_P1_UNROLL;
+constexpr int kFwdUnroll = PBR_FWD_UNROLL, kP1Unroll = PBR_P1_UNROLL, kBwdUnroll = PBR_BWD_UNROLL;
 constexpr bool kBoundaryRecompute = PBR_BOUNDARY_RECOMPUTE != 0;
 }
 #ifndef PBR_MAX_LIGHTS
@@ -375,6 +378,7 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
       for (int i = 0; i < N; ++i) g_tot[c][i] *= slope[c][i];
   }
 
+#pragma unroll kBwdUnroll
   for (int l = 0; l < L; ++l) {
     if (!two_pass) fetch(l + 1);   // light l becomes current, light l + 1 is requested
     LightGeomT<V> g[N];

@@ -61,6 +61,21 @@ VARIANTS = {
     "r2_late": v(bwd_late_prefetch=1),          # backward: next material's maps requested when the light loop is over
     "r2_sb4": v(stream_bwd_min_ctas=4),         # streamed backward capped at 128 registers (4 CTAs per SM)
     "r2_sf5": v(stream_fwd_min_ctas=5),         # streamed forward capped at 102 registers (5 CTAs per SM)
+    # round 2, second session: kFast flavour of the streamed kernels + try_wait with a suspend-time hint
+    "r3_nofast": v(stream_fast=0),                                     # hint only
+    "r3_nohint": v(wait_hint_ns=0),                                    # kFast only
+    "r3_old": v(stream_fast=0, wait_hint_ns=0),                        # neither: the code of the first session
+    "r3_bpw": v(stream_per_warp_bwd=1),                                # kFast + per-warp backward pipelines (the default since)
+    "r3_bcta": v(stream_per_warp_bwd=0),                               # kFast + CTA-level backward pipeline
+    "r3_bpw_late": v(stream_bwd_late_refill=1),
+    "r3_bpw_st3": v(stream_stages=3),
+    "r3_bpw_hm32": v(hoist_mats=32),
+    "r3_bpw_hm8": v(hoist_mats=8),
+    "r3_last": v(stream_bwd_last_refill=1),                            # kFast + the last reader of a stage refills it
+    "r3_st3": v(stream_stages=3),
+    "r3_last_st3": v(stream_bwd_last_refill=1, stream_stages=3),
+    "r3_sb4": v(stream_bwd_min_ctas=4),
+    "r3_hm32": v(hoist_mats=32),
     # memory pipeline only (no shading math): the floor of the TMA-in / STG-out design
     "nomath": ["-DPBR_DBG_NOMATH"],
 }
