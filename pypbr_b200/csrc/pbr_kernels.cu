@@ -248,10 +248,10 @@ __device__ __forceinline__ float* at(const PbrPlane& pl, int b, int c, const Whe
 template <int WF, bool kVec>
 __device__ __forceinline__ void load_material(const CtKParams& p, const Where& w, int b, float (&araw)[3][kCtTexels],
                                               float (&nraw)[3][kCtTexels], float (&rough)[kCtTexels],
-                                              float (&mraw)[3][kCtTexels]) {
+                                              float (&mraw)[3][kCtTexels], bool has_normal) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) load_seg<kCtTexels>(at<kVec>(p.albedo, b, c, w), w.vec, w.valid, araw[c]);
-  if (p.normal.ptr) {
+  if (has_normal) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) load_seg<kCtTexels>(at<kVec>(p.normal, b, c, w), w.vec, w.valid, nraw[c]);
   } else {
@@ -288,11 +288,11 @@ constexpr bool kFwdRegPrefetch = PBR_FWD_REG_PREFETCH != 0;
 __device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int WF, bool kVec>
-__device__ __forceinline__ void prefetch_material(const CtKParams& p, const Where& w, int b) {
+__device__ __forceinline__ void prefetch_material(const CtKParams& p, const Where& w, int b, bool has_normal) {
   if (!PBR_PREFETCH_NEXT || ((threadIdx.x * kCtTexels) & 31) != 0) return;   // first thread of every 128-byte line
 #pragma unroll
   for (int c = 0; c < 3; ++c) prefetch_l2(at<kVec>(p.albedo, b, c, w));
-  if (p.normal.ptr) {
+  if (has_normal) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) prefetch_l2(at<kVec>(p.normal, b, c, w));
   }
@@ -366,13 +366,42 @@ __device__ __forceinline__ void grid_coords(const CtStage& S, const Where& w, in
 #endif
 constexpr int fwd_min_ctas(int light_mode) { return is_cached(light_mode) ? PBR_FWD_CACHED_MIN_CTAS : PBR_FWD_MIN_CTAS; }
 
-template <int WF, int kLight, bool kVec = true>
+// Plain-case flavours of the generic kernels (template parameter kFM, round 2): like kFast of the streamed kernels, the host picks
+// them when the launch is what the reference's defaults produce - sRGB albedo and output, a normal map, 64-bit accesses - and
+//   kFmAccum: lights accumulated into one image (forward; backward from the saved forward output, map gradients only).
+// The switches that are warp-uniform at run time in the general flavour are constants here, so the light loop carries no
+// flag tests (8 BRA + UISETP + LDCU triples per texel-pair-light in the general code) and is one basic block to schedule:
+// static size of the backward's light loop 410 -> 190 instructions (executed: 259 -> 190), forward 147 -> 86.
+// Measured on C3 (16 x 2048^2, 16 lights): forward 3.07 -> 2.85 ms, backward 7.67 -> 6.17 ms, step 10.74 -> 9.02 ms.
+// (The same treatment of the fused fit step - per-light targets, loss, Adam epilogue as constants - was built and measured:
+// 286 instead of ~300 instructions per texel-pair-light, 255 registers with a small spill, C5 12.347 -> 12.317 ms.  That
+// kernel waits on the per-light encode / slope chains (MUFU) at 8 warps per SM, not on instruction issue: not kept.)
+
+enum { kFmGeneric = 0, kFmAccum = 1 };
+#ifndef PBR_GENERIC_FAST
+#define PBR_GENERIC_FAST 1
+#endif
+constexpr bool kGenericFast = PBR_GENERIC_FAST != 0;
+template <int kFM>
+__device__ __forceinline__ CtFlags plain_flags(const CtFlags& f) {
+  CtFlags F = f;
+  if (kFM != kFmGeneric) {
+    F.albedo_is_srgb = true; F.specular_is_srgb = true; F.return_srgb = true;
+    F.per_light = false;
+    if (kFM == kFmAccum && F.L < 2) F.L = 2;   // (never taken: the host only picks kFmAccum for L > 1; tells the compiler so)
+  }
+  return F;
+}
+
+template <int WF, int kLight, bool kVec = true, int kFM = kFmGeneric>
 __global__ void __launch_bounds__(kCtThreads, fwd_min_ctas(kLight)) ct_forward_kernel(const __grid_constant__ CtKParams p) {
   constexpr int G = PBR_FWD_GROUP;
   __shared__ CtStage S;
   stage_params(p, S);
   const Where w = locate_ct<kVec>(p);
   if (!w.active) return;
+  const CtFlags F = plain_flags<kFM>(p.flags);
+  const bool has_normal = kFM != kFmGeneric || p.normal.ptr != nullptr;
 
   V x[kSlots];
   float y;
@@ -386,7 +415,7 @@ __global__ void __launch_bounds__(kCtThreads, fwd_min_ctas(kLight)) ct_forward_k
   // are loaded into a second register set while the current one is shaded (the backward, at 235 registers, prefetches
   // into L2 instead).
   float nx_a[3][kCtTexels], nx_n[3][kCtTexels], nx_r[kCtTexels], nx_m[3][kCtTexels];
-  if (kFwdRegPrefetch) load_material<WF, kVec>(p, w, b0, nx_a, nx_n, nx_r, nx_m);
+  if (kFwdRegPrefetch) load_material<WF, kVec>(p, w, b0, nx_a, nx_n, nx_r, nx_m, has_normal);
   for (int b = b0; b < b1; ++b) {
     float araw[3][kCtTexels], nraw[3][kCtTexels], rough[kCtTexels], mraw[3][kCtTexels];
     if (kFwdRegPrefetch) {
@@ -396,10 +425,10 @@ __global__ void __launch_bounds__(kCtThreads, fwd_min_ctas(kLight)) ct_forward_k
         for (int c = 0; c < 3; ++c) { araw[c][i] = nx_a[c][i]; nraw[c][i] = nx_n[c][i]; mraw[c][i] = nx_m[c][i]; }
         rough[i] = nx_r[i];
       }
-      if (b + 1 < b1) load_material<WF, kVec>(p, w, b + 1, nx_a, nx_n, nx_r, nx_m);
+      if (b + 1 < b1) load_material<WF, kVec>(p, w, b + 1, nx_a, nx_n, nx_r, nx_m, has_normal);
     } else {
-      load_material<WF, kVec>(p, w, b, araw, nraw, rough, mraw);
-      if (b + 1 < b1) prefetch_material<WF, kVec>(p, w, b + 1);
+      load_material<WF, kVec>(p, w, b, araw, nraw, rough, mraw, has_normal);
+      if (b + 1 < b1) prefetch_material<WF, kVec>(p, w, b + 1, has_normal);
     }
     float outv[3][kCtTexels];
 #pragma unroll
@@ -410,7 +439,7 @@ __global__ void __launch_bounds__(kCtThreads, fwd_min_ctas(kLight)) ct_forward_k
 #pragma unroll
       for (int i = 0; i < G; ++i) { xs[i] = x[s + i]; hgs[i] = hg[s + i]; }
       auto emit = [&](int l, const V(&v)[3][G]) {
-        if (p.flags.per_light) {
+        if (F.per_light) {
           // one image per light: store this sub-group directly (64/128-bit when the group allows)
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
@@ -427,9 +456,9 @@ __global__ void __launch_bounds__(kCtThreads, fwd_min_ctas(kLight)) ct_forward_k
       };
       GeomCache<V> gcs = gc;   // lane-value i of the group is lane-value s + i of the thread
       gcs.base += s * gc.stride;
-      ct_forward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, emit, gcs);
+      ct_forward_group<WF, kLight, V, G>(S, F, a, n, r, m, xs, y, hgs, emit, gcs);
     }
-    if (!p.flags.per_light) {
+    if (!F.per_light) {
 #pragma unroll
       for (int c = 0; c < 3; ++c)
         store_seg<kCtTexels>(at<kVec>(p.out, b, c, w), w.vec, w.valid, outv[c]);
@@ -527,8 +556,9 @@ struct CtaGeomSink {
 
 // kGeom: also d/d(light position | direction) and d/d(view direction) (PbrCtGrads.d_lights / d_view), which the
 // reference delivers through plain autograd (cooktorrance.py:95,125-140).  Uncached per-texel light modes only.
-template <int WF, int kLight, bool kGeom = false, bool kVec = true>
+template <int WF, int kLight, bool kGeom = false, bool kVec = true, int kFM = kFmGeneric>
 __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) ct_backward_kernel(const __grid_constant__ CtKParams p) {
+  static_assert(kFM == kFmGeneric || (!kGeom && kVec), "plain-case flavours: map gradients, 64-bit accesses");
   constexpr int G = PBR_BWD_GROUP;
   __shared__ CtStage S;
   __shared__ float s_int[PBR_MAX_LIGHTS * 3];
@@ -536,8 +566,12 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
   __shared__ float s_loss[kCtThreads / 32];
   __shared__ __align__(16) float s_ring[kRing * 3 * kCtThreads * kLanes * PBR_BWD_GROUP];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const bool int_grad = p.d_intensity != nullptr;
-  const bool is_loss = p.is_loss != 0;
+  const CtFlags F = plain_flags<kFM>(p.flags);
+  const bool int_grad = kFM != kFmGeneric ? false : p.d_intensity != nullptr;
+  const bool is_loss = kFM != kFmGeneric ? false : p.is_loss != 0;
+  const bool adam_on = kFM != kFmGeneric ? false : p.adam_on != 0;
+  const bool has_normal = kFM != kFmGeneric || p.normal.ptr != nullptr;
+  const bool part_on = kFM != kFmGeneric ? false : p.part_on != 0;
   if (int_grad) {
     for (int i = tid; i < p.flags.L * 3; i += kCtThreads) s_int[i] = 0.0f;
   }
@@ -550,8 +584,8 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
   // shared-memory slots, [value][thread] (one LDS + FADD + STS, no synchronisation), over all the lights and all the
   // materials it walks over, and the CTA reduces the slots once at the end.  K values per light: 3 (intensity) or 6 (kGeom).
   constexpr int K = kGeom ? 6 : 3;
-  float* const s_part = p.part_on ? reinterpret_cast<float*>(s_dyn + p.part_smem_off) + tid : nullptr;
-  if (s_part) {
+  float* const s_part = part_on ? reinterpret_cast<float*>(s_dyn + p.part_smem_off) + tid : nullptr;
+  if (part_on) {
     for (int i = 0; i < p.flags.L * K; ++i) s_part[i * kCtThreads] = 0.0f;
   }
   stage_params(p, S);  // ends with __syncthreads()
@@ -575,7 +609,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
   // then - and land (from L2, where prefetch_material sent them) while the gradients of b are finished and stored.
   // Only where it was measured to pay: the 255-register flavour in accumulate mode (L = 16: 2.49 -> 2.45 ms per
   // 16 x 1024^2); the 168-register flavours spill over it (L = 4: 0.83 -> 1.02 ms), the per-light loss kernel is neutral.
-  const bool late_prefetch = kBwdLatePrefetch && kLight == kLightPointCached && !p.flags.per_light;
+  const bool late_prefetch = kBwdLatePrefetch && kLight == kLightPointCached && !F.per_light;
   float nx_a[3][kCtTexels], nx_n[3][kCtTexels], nx_r[kCtTexels], nx_m[3][kCtTexels];
   for (int b = b0; b < b1; ++b) {
     float araw[3][kCtTexels], nraw[3][kCtTexels], rough[kCtTexels], mraw[3][kCtTexels];
@@ -587,10 +621,10 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
         rough[i] = nx_r[i];
       }
     } else {
-      load_material<WF, kVec>(p, w, b, araw, nraw, rough, mraw);
+      load_material<WF, kVec>(p, w, b, araw, nraw, rough, mraw, has_normal);
     }
-    if (b + 1 < b1) prefetch_material<WF, kVec>(p, w, b + 1);
-    if (p.adam_on) {
+    if (b + 1 < b1) prefetch_material<WF, kVec>(p, w, b + 1, has_normal);
+    if (adam_on) {
       // Fused fit step: what the Adam epilogue of THIS material needs (parameters and both moments of every channel)
       // starts travelling now, as per-thread cp.async copies into shared memory, and lands while the light loop runs.
       // A dependent load -> update -> store chain per channel in the epilogue would expose 8 DRAM round trips per
@@ -614,7 +648,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       };
 #pragma unroll
       for (int c = 0; c < 3; ++c) send(p.albedo, 0, c);
-      if (p.normal.ptr) {
+      if (has_normal) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) send(p.normal, 1, c);
       } else {
@@ -641,9 +675,9 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       // ahead: no registers, no cross-thread synchronisation (a thread only ever reads what it copied).
       constexpr int NT = kLanes * G;
       float* ring = s_ring + tid * NT;   // [slot][channel][thread][NT]
-      const int nl_src = p.flags.per_light ? p.flags.L : 1;
+      const int nl_src = F.per_light ? F.L : 1;
       const float* const gbase = at<kVec>(p.gsrc, b, 0, w, kLanes * s);   // once per material
-      const bool have_fout = p.fout.ptr != nullptr;   // accumulate mode only (nl_src == 1): slot 1 carries the saved forward output
+      const bool have_fout = kFM == kFmAccum ? true : p.fout.ptr != nullptr;   // accumulate mode only (nl_src == 1): slot 1 carries the saved forward output
       const float* const fbase = have_fout ? at<kVec>(p.fout, b, 0, w, kLanes * s) : nullptr;
       auto issue = [&](int l) {
         const bool saved = have_fout && l == 1;
@@ -666,7 +700,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       };
       auto fetch = [&](int l) {
         if (l < 0) {   // after the light loop
-          if (late_prefetch && s + G >= kSlots && b + 1 < b1) load_material<WF, kVec>(p, w, b + 1, nx_a, nx_n, nx_r, nx_m);
+          if (late_prefetch && s + G >= kSlots && b + 1 < b1) load_material<WF, kVec>(p, w, b + 1, nx_a, nx_n, nx_r, nx_m, has_normal);
           return;
         }
         if (l == 0) {
@@ -723,7 +757,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       };
       auto int_sink = [&](int l, const float(&gi)[3]) {
         if (int_grad) {
-          if (s_part) {
+          if (part_on) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) s_part[(l * K + c) * kCtThreads] += gi[c] * live;
           } else {
@@ -739,18 +773,18 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       GeomCache<V> gcs = gc;
       gcs.base += s * gc.stride;
       if constexpr (kGeom) {
-        ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs,
+        ct_backward_group<WF, kLight, V, G>(S, F, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs,
                                             CtaGeomSink{s_geo, p.flags.L, tid, live, s_part}, CtaSavedOut{ring + 3 * (kCtThreads * NT), have_fout}, int_grad);
       } else {
-        ct_backward_group<WF, kLight, V, G>(S, p.flags, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs,
+        ct_backward_group<WF, kLight, V, G>(S, F, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch, gcs,
                                             NoGeomSink(), CtaSavedOut{ring + 3 * (kCtThreads * NT), have_fout}, int_grad);
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) { unpair_to<G>(da[c], s, d_albedo[c]); unpair_to<G>(dn[c], s, d_normal[c]); unpair_to<G>(dm[c], s, d_met[c]); }
       unpair_to<G>(dr, s, d_rough);
     }
-    if (!w.active && p.adam_on) cp_async_wait<0>();
-    if (w.active && p.adam_on) {
+    if (!w.active && adam_on) cp_async_wait<0>();
+    if (w.active && adam_on) {
       // fused fit step: the gradients never reach HBM; parameters and moments were prefetched into shared memory
       constexpr int mc = WF == 0 ? 1 : 3;
       const bool proj = p.adam_project != 0;
@@ -786,8 +820,8 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
         channel(p.albedo, 0, c, d_albedo[c], pn);
         put(p.albedo, c, pn, proj);
       }
-      if (!p.normal.ptr) ch += 3;
-      if (p.normal.ptr) {
+      if (!has_normal) ch += 3;
+      if (has_normal) {
         float pn[3][kCtTexels];
 #pragma unroll
         for (int c = 0; c < 3; ++c) channel(p.normal, 1, c, d_normal[c], pn[c]);
@@ -814,16 +848,17 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
         put(p.metspec, c, pn, proj);
       }
     } else if (w.active) {
-      if (p.d_albedo.ptr) {
+      constexpr bool kAll = kFM == kFmAccum;   // every gradient plane was requested
+      if (kAll || p.d_albedo.ptr) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) store_seg<kCtTexels>(at<kVec>(p.d_albedo, b, c, w), w.vec, w.valid, d_albedo[c]);
       }
-      if (p.normal.ptr && p.d_normal.ptr) {
+      if (kAll || (has_normal && p.d_normal.ptr)) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) store_seg<kCtTexels>(at<kVec>(p.d_normal, b, c, w), w.vec, w.valid, d_normal[c]);
       }
-      if (p.d_roughness.ptr) store_seg<kCtTexels>(at<kVec>(p.d_roughness, b, 0, w), w.vec, w.valid, d_rough);
-      if (p.d_metspec.ptr) {
+      if (kAll || p.d_roughness.ptr) store_seg<kCtTexels>(at<kVec>(p.d_roughness, b, 0, w), w.vec, w.valid, d_rough);
+      if (kAll || p.d_metspec.ptr) {
         constexpr int mc = WF == 0 ? 1 : 3;
 #pragma unroll
         for (int c = 0; c < mc; ++c) store_seg<kCtTexels>(at<kVec>(p.d_metspec, b, c, w), w.vec, w.valid, d_met[c]);
@@ -836,7 +871,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
     float sum = warp_sum(loss_local * live);
     if ((tid & 31) == 0) s_loss[tid >> 5] = sum;
   }
-  if (p.part_on) {
+  if (part_on) {
     // the per-thread slots -> the CTA's sums: warp w reduces values w, w + 4, ... (128 slots each: 4 per lane, then a shuffle)
     __syncthreads();
     const float* base = reinterpret_cast<const float*>(s_dyn + p.part_smem_off);
@@ -1250,6 +1285,18 @@ static int kernel_workflow(const PbrCtDesc* d) {
   return d->metallic_channels == 3 ? 2 : 0;
 }
 
+// what the plain-case flavour (kFmAccum) assumes besides its own mode: the reference's default colour handling and a
+// normal map, on the 64-bit-access flavour
+static bool generic_fast_disabled() {   // A/B and test switch: run the general flavour where a plain-case one would be picked
+  static const bool off = [] { const char* e = getenv("PBR_DISABLE_GENERIC_FAST"); return e && e[0] && e[0] != '0'; }();
+  return off;
+}
+template <int WF>
+static bool plain_case(const CtKParams& k) {
+  return kGenericFast && !generic_fast_disabled() && k.vec_fast && k.flags.albedo_is_srgb && k.flags.return_srgb && (WF != 1 || k.flags.specular_is_srgb) &&
+         k.normal.ptr != nullptr;
+}
+
 template <int WF>
 static void launch_fwd(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t st) {
   const int lm = light_mode(k, false);
@@ -1258,11 +1305,21 @@ static void launch_fwd(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t s
     else ct_forward_kernel<WF, kLightPoint, false><<<grid, block, 0, st>>>(k);
     return;
   }
+  const bool accum = plain_case<WF>(k) && !k.flags.per_light;   // the kFmAccum flavour applies
   switch (lm) {
     case kLightDirectional: ct_forward_kernel<WF, kLightDirectional><<<grid, block, 0, st>>>(k); break;
-    case kLightPoint: ct_forward_kernel<WF, kLightPoint><<<grid, block, 0, st>>>(k); break;
-    case kLightPointCached: launch_dyn<ct_forward_kernel<WF, kLightPointCached>>(k, grid, block, geom_cache_bytes(k.flags.L, kLightPointCached), st); break;
-    case kLightPointCachedAll: launch_dyn<ct_forward_kernel<WF, kLightPointCachedAll>>(k, grid, block, geom_cache_bytes(k.flags.L, kLightPointCachedAll), st); break;
+    case kLightPoint:
+      if (accum && k.flags.L > 1) ct_forward_kernel<WF, kLightPoint, true, kFmAccum><<<grid, block, 0, st>>>(k);
+      else ct_forward_kernel<WF, kLightPoint><<<grid, block, 0, st>>>(k);
+      break;
+    case kLightPointCached:
+      if (accum) launch_dyn<ct_forward_kernel<WF, kLightPointCached, true, kFmAccum>>(k, grid, block, geom_cache_bytes(k.flags.L, kLightPointCached), st);
+      else launch_dyn<ct_forward_kernel<WF, kLightPointCached>>(k, grid, block, geom_cache_bytes(k.flags.L, kLightPointCached), st);
+      break;
+    case kLightPointCachedAll:
+      if (accum) launch_dyn<ct_forward_kernel<WF, kLightPointCachedAll, true, kFmAccum>>(k, grid, block, geom_cache_bytes(k.flags.L, kLightPointCachedAll), st);
+      else launch_dyn<ct_forward_kernel<WF, kLightPointCachedAll>>(k, grid, block, geom_cache_bytes(k.flags.L, kLightPointCachedAll), st);
+      break;
     default: ct_forward_kernel<WF, kLightPointHoisted><<<grid, block, 0, st>>>(k); break;
   }
 }
@@ -1303,12 +1360,27 @@ static void launch_bwd(const CtKParams& k_in, dim3 grid, dim3 block, cudaStream_
     else launch_dyn<ct_backward_kernel<WF, kLightPoint, false, false>>(k, grid, block, smem, st);
     return;
   }
+  // the kFmAccum flavour: what autograd asks for after an accumulated render (every map gradient, the saved output handed in)
+  const bool accum = plain_case<WF>(k) && !k.flags.per_light && k.flags.L > 1 && !k.is_loss && !k.adam_on && !k.d_intensity &&
+                     k.fout.ptr && k.d_albedo.ptr && k.d_normal.ptr && k.d_roughness.ptr && k.d_metspec.ptr;
   switch (lm) {
     case kLightDirectional: launch_dyn<ct_backward_kernel<WF, kLightDirectional>>(k, grid, block, smem, st); break;
-    case kLightPoint: launch_dyn<ct_backward_kernel<WF, kLightPoint>>(k, grid, block, smem, st); break;
-    case kLightPointCached: launch_dyn<ct_backward_kernel<WF, kLightPointCached>>(k, grid, block, smem, st); break;
-    case kLightPointCachedAll: launch_dyn<ct_backward_kernel<WF, kLightPointCachedAll>>(k, grid, block, smem, st); break;
-    case kLightPointCachedAllBig: launch_dyn<ct_backward_kernel<WF, kLightPointCachedAllBig>>(k, grid, block, smem, st); break;
+    case kLightPoint:
+      if (accum) launch_dyn<ct_backward_kernel<WF, kLightPoint, false, true, kFmAccum>>(k, grid, block, smem, st);
+      else launch_dyn<ct_backward_kernel<WF, kLightPoint>>(k, grid, block, smem, st);
+      break;
+    case kLightPointCached:
+      if (accum) launch_dyn<ct_backward_kernel<WF, kLightPointCached, false, true, kFmAccum>>(k, grid, block, smem, st);
+      else launch_dyn<ct_backward_kernel<WF, kLightPointCached>>(k, grid, block, smem, st);
+      break;
+    case kLightPointCachedAll:
+      if (accum) launch_dyn<ct_backward_kernel<WF, kLightPointCachedAll, false, true, kFmAccum>>(k, grid, block, smem, st);
+      else launch_dyn<ct_backward_kernel<WF, kLightPointCachedAll>>(k, grid, block, smem, st);
+      break;
+    case kLightPointCachedAllBig:
+      if (accum) launch_dyn<ct_backward_kernel<WF, kLightPointCachedAllBig, false, true, kFmAccum>>(k, grid, block, smem, st);
+      else launch_dyn<ct_backward_kernel<WF, kLightPointCachedAllBig>>(k, grid, block, smem, st);
+      break;
     default: launch_dyn<ct_backward_kernel<WF, kLightPointHoisted>>(k, grid, block, smem, st); break;
   }
 }
@@ -1371,7 +1443,8 @@ static void stream_launch(const CtKParams& k, dim3 grid, dim3 block, int planes,
 template <int WF>
 static void launch_fwd_stream(const CtKParams& k, dim3 grid, dim3 block, cudaStream_t st) {
   const int planes = k.normal.ptr ? Slots<WF, false>::count : Slots<WF, false>::count_no_normal;
-  const bool fast = kStreamFast && block.x == (unsigned)kStreamThreads && block.y == 1 && (k.W % kTileFloats) == 0 && k.normal.ptr;
+  const bool fast = kStreamFast && block.x == (unsigned)kStreamThreads && block.y == 1 && (k.W % kTileFloats) == 0 && k.normal.ptr &&
+                    k.flags.albedo_is_srgb && k.flags.return_srgb && (WF != 1 || k.flags.specular_is_srgb);
   if (fast) {
     if (k.flags.point) stream_launch<ct_forward_stream<WF, kLightPointHoisted, true>>(k, grid, block, planes, st);
     else stream_launch<ct_forward_stream<WF, kLightDirectional, true>>(k, grid, block, planes, st);
@@ -1386,6 +1459,7 @@ static void launch_bwd_stream_m(const CtKParams& k, dim3 grid, dim3 block, cudaS
   const int planes = k.normal.ptr ? Slots<WF, true>::count : Slots<WF, true>::count_no_normal;
   // the plain case (full tiles of one row, a normal map, every gradient requested) runs the kFast flavour (pbr_ct_stream.cuh)
   const bool fast = kStreamFast && block.x == (unsigned)kStreamThreads && block.y == 1 && (k.W % kTileFloats) == 0 && k.normal.ptr &&
+                    k.flags.albedo_is_srgb && k.flags.return_srgb && (WF != 1 || k.flags.specular_is_srgb) &&
                     k.d_albedo.ptr && k.d_normal.ptr && k.d_roughness.ptr && k.d_metspec.ptr;
   if (fast) {
     if (k.flags.point) stream_launch<ct_backward_stream<WF, kLightPointHoisted, kMode, true>>(k, grid, block, planes, st);

@@ -128,6 +128,9 @@ def _random_case(seed, B, H, W, L, workflow="metallic", rough_lo=0.2, normal=Tru
     (17, 4, 24, 12, True, "metallic"),    # geometry cache at 12 lights
     (3, 6, 24, 20, True, "metallic"),     # more lights than the cache takes: per-texel geometry, one material per CTA
     (2, 5, 20, 18, False, "specular"),    # ... per-light outputs
+    (None, 16, 64, 6, True, "metallic"),  # ONE material under several lights: per-texel geometry, plain-case (kFmAccum) flavour
+    (4, 8, 64, 3, True, "specular"),      # all-8-field cache, specular workflow, plain-case flavour
+    (5, 6, 32, 7, True, "metallic"),      # 4 < L <= 8: forward on the 6-field cache, backward on the big all-field cache
 ])
 def test_against_oracle_seeded(B, H, W, L, acc, wf, ct_path):
     """Fresh seeded inputs (not in the fixtures) against the oracle run on the host."""
