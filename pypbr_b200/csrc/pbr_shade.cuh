@@ -191,7 +191,7 @@ PBR_HD V encode_out_d(V c, bool return_srgb, V* d) {
 // forward: N lane-values of one row.  emit(l, out[3][N]) receives the encoded colour of light l
 // (per-light mode) or, once, of the accumulated image (l = 0).
 // ------------------------------------------------------------------------------------------------
-template <int kWorkflow, int kLight, class V, int N, class Emit>
+template <int kWorkflow, int kLight, class V, int N, class Emit, int kUnroll = kFwdUnroll>
 PBR_HD void ct_forward_group(const CtStage& S, const CtFlags& F, const V (&araw)[3][N], const V (&nraw)[3][N],
                              const V (&rough)[N], const V (&mraw)[3][N], const V (&x)[N], float y,
                              const LightGeomT<V> (&hoisted)[N], Emit emit, GeomCache<V> gc = GeomCache<V>()) {
@@ -210,7 +210,7 @@ PBR_HD void ct_forward_group(const CtStage& S, const CtFlags& F, const V (&araw)
     for (int i = 0; i < N; ++i) acc[c][i] = splat<V>(0.0f);
 
   const int L = (kLight == kLightPointHoisted) ? 1 : F.L;
-#pragma unroll kFwdUnroll
+#pragma unroll kUnroll
   for (int l = 0; l < L; ++l) {
     V outv[3][N];
 #pragma unroll
@@ -291,7 +291,7 @@ PBR_HD V encode_slope_from_out(V out, bool return_srgb) {
 }
 
 template <int kWorkflow, int kLight, class V, int N, class Gout, class IntSink, class Fetch = NoFetch,
-          class GeomSink = NoGeomSink, class SavedOut = NoSavedOut>
+          class GeomSink = NoGeomSink, class SavedOut = NoSavedOut, int kUnroll = kBwdUnroll>
 PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw)[3][N], const V (&nraw)[3][N],
                               const V (&rough)[N], const V (&mraw)[3][N], const V (&x)[N], float y,
                               const LightGeomT<V> (&hoisted)[N], Gout gout, IntSink int_sink, V (&d_albedo)[3][N],
@@ -378,7 +378,7 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
       for (int i = 0; i < N; ++i) g_tot[c][i] *= slope[c][i];
   }
 
-#pragma unroll kBwdUnroll
+#pragma unroll kUnroll
   for (int l = 0; l < L; ++l) {
     if (!two_pass) fetch(l + 1);   // light l becomes current, light l + 1 is requested
     LightGeomT<V> g[N];

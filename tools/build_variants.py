@@ -76,6 +76,13 @@ VARIANTS = {
     "r3_last_st3": v(stream_bwd_last_refill=1, stream_stages=3),
     "r3_sb4": v(stream_bwd_min_ctas=4),
     "r3_hm32": v(hoist_mats=32),
+    # light-loop unrolling on top of the plain-case (single basic block) flavour of the generic kernels
+    "r3_fu2": v(fwd_unroll=2),
+    "r3_fu4": v(fwd_unroll=4),
+    "r3_bu2": v(bwd_unroll=2),
+    "r3_fu2_f3": v(fwd_unroll=2, fwd_cached_min_ctas=3),
+    "r3_f3": v(fwd_cached_min_ctas=3),
+    "r3_b3": v(bwd_cached_min_ctas=3),
     # memory pipeline only (no shading math): the floor of the TMA-in / STG-out design
     "nomath": ["-DPBR_DBG_NOMATH"],
 }

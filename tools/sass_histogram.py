@@ -10,9 +10,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "pypbr_b200", "lib", "libpbrcuda.so")
-want = [re.compile(p) for p in (sys.argv[1:] or [r"ct_forward_stream<0, 2>", r"ct_backward_stream<0, 2, 0>", r"ct_backward_stream<0, 2, 1>",
-                                                 r"ct_forward_kernel<0, 3, true>", r"ct_backward_kernel<0, 3, false, true>",
-                                                 r"ct_backward_kernel<0, 5, false, true>", r"convert_kernel", r"convert_bwd_kernel",
+want = [re.compile(p) for p in (sys.argv[1:] or [r"ct_forward_stream<0, 2, true>", r"ct_backward_stream<0, 2, 0, true>", r"ct_backward_stream<0, 2, 1, true>",
+                                                 r"ct_backward_stream<0, 2, 0, false>",
+                                                 r"ct_forward_kernel<0, 3, true, 1>", r"ct_backward_kernel<0, 3, false, true, 1>",
+                                                 r"ct_backward_kernel<0, 3, false, true, 0>", r"ct_backward_kernel<0, 5, false, true, 0>",
+                                                 r"convert_kernel", r"convert_bwd_kernel",
                                                  r"blend_kernel", r"blend_bwd_kernel", r"ingest_kernel<3, 8>", r"index_transform_kernel",
                                                  r"adam_kernel", r"normal_op_kernel", r"normal_ingest"])]
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
