@@ -10,8 +10,12 @@
 //   tile    = blockDim.y rows x (blockDim.x * kST) texels of ONE material: every input plane of the tile
 //             (albedo x3, roughness, metallic | specular, normal x3, and grad_out | target x3 for the
 //             backward) is kTileFloats contiguous floats of shared memory per stage, in image order;
-//   producer= warp 0: one cp.async.bulk per (plane, row) -> stage buffer, completion counted in bytes
-//             on the stage's mbarrier (pbr_async.cuh);
+//   producer= every warp for itself (per-warp pipelines, the default for both kernels): a warp owns 32 x kST contiguous texels
+//             of the tile row, i.e. one cp.async.bulk of 512 B per plane and stage, completion counted in bytes on the
+//             warp's own mbarrier (pbr_async.cuh); right after it has read a stage into registers one lane per plane
+//             re-arms the barrier and issues the copies of the tile kStages ahead.  No cross-warp synchronisation at all.
+//             (PBR_STREAM_PER_WARP_*=0 builds the CTA-level pipeline instead: warp 0 feeds the whole CTA, one copy per
+//             (plane, row), and waits on an "empty" mbarrier the other warps arrive on after their last read.)
 //   consumer= all threads.  A thread owns kSSlots lane-values (texel pairs) of one tile row, INTERLEAVED
 //             with the other threads of the row: slot j of thread tx covers the texels
 //             j*(bx*kLanes) + tx*kLanes ... + kLanes-1 of the row.  So one warp-level LDS.64 / STG.64
@@ -19,17 +23,16 @@
 //             the way out.  The forward kernel shades all of a thread's slots together (ILP); the
 //             backward takes them one at a time - inputs come out of the stage right before they are
 //             used and the gradients leave right after, so only one pair's working set is live in
-//             registers (the adjoint needs ~170 of them).  After its last read of a stage a warp
-//             arrives once on the stage's "empty" mbarrier; warp 0 waits for it (complete in practice)
-//             and refills the stage with the tile that is kStages ahead.  No CTA-wide barrier in the loop.
+//             registers (the adjoint needs ~170 of them).  No CTA-wide barrier in the loop.
 //
 // A CTA walks over `mats_per_cta` materials at a fixed image position, so for a point light the
 // per-texel light geometry (material independent) is computed once and reused - as in the generic
 // kernels - and the pipeline stays full for the whole walk.
 //
 // Measured floor of this data-movement design with the shading math compiled out (-DPBR_DBG_NOMATH,
-// tools/build_variants.py): 6.4-6.5 TB/s forward and backward, i.e. 98-99 % of the measured copy peak;
-// whatever the real kernels lose against that is instruction issue, not memory.
+// tools/build_variants.py): 6.4-6.6 TB/s forward and backward, i.e. 98-100 % of the measured copy peak;
+// whatever the real kernels lose against that is instruction issue, not memory.  With the kFast flavour (below) they
+// lose almost nothing: forward 0.446-0.451 ms (100 %), backward 0.783-0.807 ms (96-99 %) at 64 x 1024^2.
 #pragma once
 
 #include "pbr_async.cuh"

@@ -511,6 +511,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 constexpr int bwd_min_ctas(int light_mode) {
   return (light_mode == kLightPointCached || light_mode == kLightPointCachedAllBig) ? PBR_BWD_CACHED_MIN_CTAS : PBR_BWD_MIN_CTAS;
 }
+// Light-loop unrolling of the general backward: by two where the full register budget is available (per-light loss kernel,
+// 32 x 1024^2: L = 8 2.654 -> 2.571 ms, L = 16 2.470 -> 2.393 ms; the 168-register flavours spill over it: L = 4 1.624 -> 1.794 ms).
+#ifndef PBR_BWD_BIG_UNROLL
+#define PBR_BWD_BIG_UNROLL 2
+#endif
+PBR_HDC int bwd_unroll(int light_mode) {
+  return (light_mode == kLightPointCached || light_mode == kLightPointCachedAllBig) ? PBR_BWD_BIG_UNROLL : kBwdUnroll;
+}
 
 // The saved forward output of the row segment being back-propagated (PbrCtGrads.fwd_out).  It travels through slot 1 of
 // the thread's cp.async ring (accumulate mode keeps only slot 0 busy, with grad_out), requested together with grad_out
@@ -590,7 +598,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
   // materials it walks over, and the CTA reduces the slots once at the end.  K values per light: 3 (intensity) or 6 (kGeom).
   constexpr int K = kGeom ? 6 : 3;
   float* const s_part = part_on ? reinterpret_cast<float*>(s_dyn + p.part_smem_off) + tid : nullptr;
-  if (part_on) {
+  if (s_part) {
     for (int i = 0; i < p.flags.L * K; ++i) s_part[i * kCtThreads] = 0.0f;
   }
   stage_params(p, S);  // ends with __syncthreads()
@@ -762,7 +770,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       };
       auto int_sink = [&](int l, const float(&gi)[3]) {
         if (int_grad) {
-          if (part_on) {
+          if (s_part) {   // (the same test as CtaGeomSink's: one uniform branch per light for both)
 #pragma unroll
             for (int c = 0; c < 3; ++c) s_part[(l * K + c) * kCtThreads] += gi[c] * live;
           } else {
@@ -783,7 +791,7 @@ __global__ void __launch_bounds__(kCtThreads, kGeom ? 2 : bwd_min_ctas(kLight)) 
       } else {
         // (plain-case flavour, light loop unrolled by two: L = 16 1.570 -> 1.549 ms, L = 8 0.916 -> 0.886 ms per 16 x 1024^2)
         ct_backward_group<WF, kLight, V, G, decltype(gout), decltype(int_sink), decltype(fetch), NoGeomSink, CtaSavedOut,
-                          (kFM != kFmGeneric ? kPlainUnroll : kBwdUnroll)>(S, F, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch,
+                          (kFM != kFmGeneric ? kPlainUnroll : bwd_unroll(kLight))>(S, F, a, n, r, m, xs, y, hgs, gout, int_sink, da, dn, dr, dm, fetch,
                                                                           gcs, NoGeomSink(), CtaSavedOut{ring + 3 * (kCtThreads * NT), have_fout}, int_grad);
       }
 #pragma unroll

@@ -81,6 +81,7 @@ VARIANTS = {
     "r3_fu4": v(fwd_unroll=4),
     "r3_bu2": v(bwd_unroll=2),
     "r3_fu2_f3": v(fwd_unroll=2, fwd_cached_min_ctas=3),
+    "r3_gbu2": v(bwd_unroll=2),               # general flavour of the backward (the per-light loss / fit kernels), light loop unrolled by two
     "r3_f3": v(fwd_cached_min_ctas=3),
     "r3_b3": v(bwd_cached_min_ctas=3),
     # memory pipeline only (no shading math): the floor of the TMA-in / STG-out design
