@@ -1233,3 +1233,83 @@ def test_rendering_loss_module_shapes_and_no_grad():
         l2 = crit(pred, gtm)
     assert not l2.requires_grad and abs(float(l2) - float(loss)) <= 1e-6 * float(loss)
     assert torch.cuda.memory_allocated() - before < 64 * 1024   # no gradient buffers (4 maps x 20 x 28 would be far below; guards growth)
+
+
+# ---------------------------------------------------------------------------------------------- kernel-flavour dispatch
+def _dispatch_cases():
+    """Deterministic sweep over what decides the kernel flavour ('Kernel selection'): tile-filling widths
+    (W % 512 == 0 -> kFast), lights (1 -> streamed; 2..4, 5..8, 9..16 -> the three geometry caches; one material ->
+    per-texel geometry), colour flags, a missing normal map, per-light output, which leaves want gradients, row-strided
+    views of wider tensors (16-byte aligned: still eligible for the fast flavours) and a batch-broadcast roughness."""
+    cases = []
+    i = 0
+    for W in (512, 1024):
+        for L in (1, 3, 6, 9):
+            for B in ((None, 2, 17) if L == 1 else (1, 3)):
+                i += 1
+                cases.append(dict(
+                    W=W, H=2 + i % 2, L=L, B=B,
+                    wf="specular" if i % 3 == 0 else "metallic",
+                    normal=i % 5 != 0,
+                    albedo_is_srgb=i % 7 != 0,
+                    return_srgb=i % 4 != 1,
+                    per_light=(L > 1 and i % 6 == 2),
+                    light_type="directional" if i % 8 == 3 else "point",
+                    grads="all" if i % 3 != 1 else "some",
+                    strided=i % 2 == 0,
+                    broadcast_rough=(B not in (None, 1) and i % 4 == 2),
+                ))
+    return cases
+
+
+@pytest.mark.parametrize("c", _dispatch_cases(), ids=lambda c: "W{W}_L{L}_B{B}_{wf}_{light_type}".format(**c))
+def test_kernel_flavour_dispatch_against_oracle(c):
+    """Every automatic kernel choice - kFast or general streamed kernels, plain-case or general multi-light kernels - computes
+    the reference's function: forward and the requested gradients against the oracle on tile-filling widths."""
+    from oracle import pbr_oracle as O
+
+    B, H, W, L = c["B"], c["H"], c["W"], c["L"]
+    maps, lights, inten, g = _random_case(4200 + W + 13 * L + (B or 0), B, H, W, L, c["wf"], normal=c["normal"])
+    if c["broadcast_rough"]:
+        # one roughness map shared by the whole batch: the reference semantics are the same values for every material
+        maps["roughness"] = maps["roughness"][:1].expand_as(maps["roughness"]).clone()
+    if c["light_type"] == "directional":
+        lights = torch.nn.functional.normalize(lights + torch.tensor([0.0, 0.0, 1.0]), dim=-1)
+    view = torch.tensor([0.03, -0.08, 1.0])
+    size = 1.0 if c["light_type"] == "point" else None
+    flags = dict(albedo_is_srgb=c["albedo_is_srgb"], specular_is_srgb=True, return_srgb=c["return_srgb"])
+    want = set(maps) if c["grads"] == "all" else {"albedo", "roughness"}
+
+    leaves_ref = {k: v.clone().requires_grad_(k in want) for k, v in maps.items()}
+    ref = O.render(leaves_ref, view, lights, inten, size, c["light_type"], accumulate=not c["per_light"], **flags)
+    go = torch.rand(ref.shape, generator=g)
+    ref.backward(go)
+
+    p = dict(light_type=c["light_type"], albedo_is_srgb=c["albedo_is_srgb"])
+    mat, _ = _material(maps, p)
+    leaves = {}
+    for k, v in maps.items():
+        t = v.to(DEV)
+        if c["broadcast_rough"] and k == "roughness":
+            t = t[:1].contiguous()           # (1, 1, H, W): batch stride 0 once the host expands it
+        elif c["strided"]:
+            wide = torch.zeros(*t.shape[:-1], W + 8, device=DEV)
+            wide[..., 4:W + 4] = t
+            t = wide[..., 4:W + 4]           # row stride W + 8, first texel 16-byte aligned
+        t = t.detach().requires_grad_(k in want)
+        leaves[k] = t
+        mat._maps[k] = t
+    out = _brdf(p, c["per_light"])(mat, view, lights, inten, size, c["return_srgb"])
+    assert out.shape == ref.shape
+    ratio, ok = fwd_ok(out.detach().cpu().numpy(), ref.detach().numpy())
+    assert ok, f"forward {ratio}"
+    out.backward(go.to(DEV))
+    for k in want & set(maps):
+        got, exp = leaves[k].grad, leaves_ref[k].grad
+        if c["broadcast_rough"] and k == "roughness":
+            exp = exp.sum(0, keepdim=True)   # the shared map collects every material's gradient
+        assert got is not None, k
+        ratio, ok = grad_ok(got.cpu().numpy(), exp.numpy())
+        assert ok, f"d_{k} {ratio}"
+    for k in set(maps) - want:
+        assert leaves[k].grad is None
