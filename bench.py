@@ -1166,6 +1166,18 @@ def run_aux(args):
         add("flip_horizontal, 4 maps (8 channels) in one gather", timed(flip), texels * 8 * 8)
         add("roll, 4 maps (8 channels) in one gather", timed(rollit), texels * 8 * 8)
         reset()
+        # the functional transform a user calls (pypbr_b200.transforms): a NEW material, the source untouched.  It starts from a
+        # tensor-sharing copy, so the step moves 8 B per channel-texel; the reference's scheme (deep clone, then the method on
+        # the clone) moves 16.
+        from pypbr_b200.transforms import functional as TFn
+
+        add("transforms.functional.flip_horizontal (public API, new material)", timed(lambda: TFn.flip_horizontal(mat)), texels * 8 * 8)
+
+        def clone_then_flip():
+            m2 = mat.clone()
+            m2.flip_horizontal()
+
+        add("clone() + flip_horizontal() (the reference's scheme, same kernels)", timed(clone_then_flip), texels * 8 * 8)
         opt = FusedAdam({k: v for k, v in maps.items()}, lr=1e-3)
         grads = {k: torch.rand_like(v) for k, v in maps.items()}
         add("Adam + projection, 4 maps (8 channels)", timed(lambda: opt.step(grads)), texels * 8 * 28)
