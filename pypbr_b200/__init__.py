@@ -7,8 +7,8 @@ The arithmetic runs in hand-written CUDA kernels reached through a C ABI (includ
 no CPU path in this package.
 """
 
-from . import blending, materials, models, transforms, utils
+from . import blending, io, materials, models, transforms, utils
 
 __version__ = "0.1.0"
 
-__all__ = ["blending", "materials", "models", "transforms", "utils"]
+__all__ = ["blending", "io", "materials", "models", "transforms", "utils"]

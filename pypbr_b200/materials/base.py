@@ -512,7 +512,10 @@ class MaterialBase:
         return out
 
     def save_to_folder(self, folder_path: str):
-        raise NotImplementedError("pypbr_b200: disk IO is outside the shading hot path (SURVEY.md §2 #10).")
+        """Save the maps as images (base.py:869-878 -> pypbr/io.py:189-230)."""
+        from ..io import save_material_to_folder
+
+        save_material_to_folder(self, folder_path)
 
     # ------------------------------------------------------------------ misc
     def __repr__(self):
