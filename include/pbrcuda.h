@@ -309,16 +309,24 @@ typedef struct PbrAdamDesc {
  *                map, `out` = the gradient w.r.t. the height map (1 ch):
  *                d_h[y,x] = scale * (a[y,x+1] - a[y,x-1] + b[y+1,x] - b[y-1,x]) with a = -g_u.x, b = -+g_u.y of the neighbour texel,
  *                g_u the gradient pushed through that texel's normalisation (recomputed), zero outside the image.
+ *   ROTATE_BWD : the adjoint of ROTATE (the reference's rotation is a matmul + F.normalize on a tensor autograd tracks; with
+ *                cos_a = strength, sin_a = 0 it is the adjoint of MaterialBase.adjust_normal_strength, base.py:689-706):
+ *                `in` = the normal map BEFORE the rotation (3 ch), `aux` = the gradient w.r.t. the rotated map (3 ch),
+ *                `out` = the gradient w.r.t. `in` (3 ch); in, aux and out must not overlap.
+ *   DIVERGENCE_BWD: the adjoint of DIVERGENCE: `in` = the normal map (3 ch), `aux` = the gradient w.r.t. the divergence (1 ch),
+ *                `out` = the gradient w.r.t. the normal map (3 ch).  (The Poisson solve and the [0,1] normalisation around it
+ *                are differentiable library calls on the caller's side.)
  */
-enum { PBR_NORMAL_OP_ROTATE = 0, PBR_NORMAL_OP_FROM_HEIGHT = 1, PBR_NORMAL_OP_DIVERGENCE = 2, PBR_NORMAL_OP_FROM_HEIGHT_BWD = 3 };
+enum { PBR_NORMAL_OP_ROTATE = 0, PBR_NORMAL_OP_FROM_HEIGHT = 1, PBR_NORMAL_OP_DIVERGENCE = 2, PBR_NORMAL_OP_FROM_HEIGHT_BWD = 3,
+       PBR_NORMAL_OP_ROTATE_BWD = 4, PBR_NORMAL_OP_DIVERGENCE_BWD = 5 };
 typedef struct PbrNormalOpDesc {
   int32_t B, H, W;
   int32_t op;               /* PBR_NORMAL_OP_* */
-  float cos_a, sin_a;       /* ROTATE */
-  float scale;              /* FROM_HEIGHT, DIVERGENCE */
-  int32_t flip_y;           /* FROM_HEIGHT, DIVERGENCE: 1 = NormalConvention.DIRECTX */
+  float cos_a, sin_a;       /* ROTATE, ROTATE_BWD */
+  float scale;              /* FROM_HEIGHT, DIVERGENCE and their adjoints */
+  int32_t flip_y;           /* FROM_HEIGHT, DIVERGENCE and their adjoints: 1 = NormalConvention.DIRECTX */
   PbrPlane in, out;         /* out: 3 ch (DIVERGENCE, FROM_HEIGHT_BWD: 1 ch) */
-  PbrPlane aux;             /* FROM_HEIGHT_BWD: gradient w.r.t. the normal map (3 ch); otherwise unused */
+  PbrPlane aux;             /* the adjoints: the incoming gradient (FROM_HEIGHT_BWD, ROTATE_BWD: 3 ch; DIVERGENCE_BWD: 1 ch); otherwise unused */
 } PbrNormalOpDesc;
 
 /*

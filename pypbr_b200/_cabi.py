@@ -172,6 +172,7 @@ class PbrNormalOpDesc(Structure):
 
 
 NORMAL_OP_ROTATE, NORMAL_OP_FROM_HEIGHT, NORMAL_OP_DIVERGENCE, NORMAL_OP_FROM_HEIGHT_BWD = 0, 1, 2, 3
+NORMAL_OP_ROTATE_BWD, NORMAL_OP_DIVERGENCE_BWD = 4, 5
 
 # order = the `which` argument of pbr_sizeof()
 STRUCTS = (PbrPlane, PbrCtDesc, PbrCtGrads, PbrCtLoss, PbrConvDesc, PbrBlendMap, PbrBlendDesc, PbrColorDesc, PbrNormalDesc,

@@ -317,6 +317,55 @@ __global__ void __launch_bounds__(kThreads) normal_op_kernel(const __grid_consta
     store_seg<kTexels>(d.out.ptr + plane_off(d.out, w.b, 0, w.row, w.col0), w.vec, w.valid, dh);
     return;
   }
+  if (d.op == PBR_NORMAL_OP_ROTATE_BWD) {
+    // y = normalize(R (x, y), z): d_in = R^T-applied gradient pushed through the normalisation (recomputed from `in`, the map
+    // BEFORE the rotation).  cos_a = strength, sin_a = 0 is the adjoint of adjust_normal_strength.
+    float v[3][kTexels], g[3][kTexels];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      load_seg<kTexels>(d.in.ptr + plane_off(d.in, w.b, c, w.row, w.col0), w.vec, w.valid, v[c]);
+      load_seg<kTexels>(d.aux.ptr + plane_off(d.aux, w.b, c, w.row, w.col0), w.vec, w.valid, g[c]);
+    }
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i) {
+      const float u[3] = {xfma(v[1][i], -d.sin_a, xmul(v[0][i], d.cos_a)), xfma(v[1][i], d.cos_a, xmul(v[0][i], d.sin_a)), v[2][i]};
+      const float gi[3] = {g[0][i], g[1][i], g[2][i]};
+      float gu[3];
+      normalize3_bwd(u, gi, gu);
+      o[0][i] = gu[0] * d.cos_a + gu[1] * d.sin_a;
+      o[1][i] = gu[1] * d.cos_a - gu[0] * d.sin_a;
+      o[2][i] = gu[2];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) store_seg<kTexels>(d.out.ptr + plane_off(d.out, w.b, c, w.row, w.col0), w.vec, w.valid, o[c]);
+    return;
+  }
+  if (d.op == PBR_NORMAL_OP_DIVERGENCE_BWD) {
+    // div[y][x] = gx[y][min(x+1, W-1)] - gx[y][x] + gy[min(y+1, H-1)][x] - gy[y][x] with gx = -Nx r s, gy = -+Ny r s, r = 1/(Nz + 1e-8):
+    //   A = d/d gx[y][x] = G[y][x-1] (x >= 1) + G[y][W-1] (x == W-1) - G[y][x],  B = d/d gy[y][x] likewise along y  (G = `aux`)
+    //   d_Nx = -r s A,  d_Ny = sy r s B (sy = +1 DirectX, -1 OpenGL),  d_Nz = r^2 s (Nx A - sy Ny B)
+    const float* G = d.aux.ptr + plane_off(d.aux, w.b, 0, 0, 0);
+    const float sy = d.flip_y ? 1.0f : -1.0f;
+    float n[3][kTexels];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) load_seg<kTexels>(d.in.ptr + plane_off(d.in, w.b, c, w.row, w.col0), w.vec, w.valid, n[c]);
+#pragma unroll
+    for (int i = 0; i < kTexels; ++i) {
+      const int x = min(w.col0 + i, d.W - 1), y = w.row;
+      const float* Gr = G + (int64_t)y * d.aux.sh;
+      const float g0 = __ldg(Gr + x);
+      const float A = (x >= 1 ? __ldg(Gr + x - 1) : 0.0f) + (x == d.W - 1 ? g0 : 0.0f) - g0;
+      const float B = (y >= 1 ? __ldg(Gr - d.aux.sh + x) : 0.0f) + (y == d.H - 1 ? g0 : 0.0f) - g0;
+      const float r = 1.0f / (n[2][i] + 1e-8f);
+      const float rs = r * d.scale;
+      o[0][i] = -rs * A;
+      o[1][i] = sy * rs * B;
+      o[2][i] = r * rs * (n[0][i] * A - sy * n[1][i] * B);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) store_seg<kTexels>(d.out.ptr + plane_off(d.out, w.b, c, w.row, w.col0), w.vec, w.valid, o[c]);
+    return;
+  }
   if (d.op == PBR_NORMAL_OP_ROTATE) {
     float v[3][kTexels];
 #pragma unroll

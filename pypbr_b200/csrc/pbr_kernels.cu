@@ -1898,13 +1898,15 @@ int pbr_adam_step(const PbrAdamDesc* d, pbr_stream_t stream) {
 int pbr_normal_op(const PbrNormalOpDesc* d, pbr_stream_t stream) {
   if (!d) return PBR_E_NULL;
   if (int rc = check_dims(d->B, d->H, d->W)) return rc;
-  if (d->op < PBR_NORMAL_OP_ROTATE || d->op > PBR_NORMAL_OP_FROM_HEIGHT_BWD) return PBR_E_ENUM;
+  if (d->op < PBR_NORMAL_OP_ROTATE || d->op > PBR_NORMAL_OP_DIVERGENCE_BWD) return PBR_E_ENUM;
   if (!d->in.ptr || !d->out.ptr) return PBR_E_NULL;
-  if (d->op == PBR_NORMAL_OP_FROM_HEIGHT_BWD && !d->aux.ptr) return PBR_E_NULL;
-  if (d->op != PBR_NORMAL_OP_ROTATE && d->in.ptr == d->out.ptr) return PBR_E_NULL;   // a stencil cannot run in place
+  const bool adjoint = d->op == PBR_NORMAL_OP_FROM_HEIGHT_BWD || d->op == PBR_NORMAL_OP_ROTATE_BWD || d->op == PBR_NORMAL_OP_DIVERGENCE_BWD;
+  if (adjoint && (!d->aux.ptr || d->aux.ptr == d->out.ptr)) return PBR_E_NULL;
+  if (d->op != PBR_NORMAL_OP_ROTATE && d->in.ptr == d->out.ptr) return PBR_E_NULL;   // a stencil / an adjoint cannot run in place
   NormalOpKParams k{};
   k.d = *d;
-  k.vec_ok = plane_vec_ok(d->out) && (d->op != PBR_NORMAL_OP_ROTATE || plane_vec_ok(d->in));
+  const bool row_loads = d->op == PBR_NORMAL_OP_ROTATE || d->op == PBR_NORMAL_OP_ROTATE_BWD || d->op == PBR_NORMAL_OP_DIVERGENCE_BWD;
+  k.vec_ok = plane_vec_ok(d->out) && (!row_loads || plane_vec_ok(d->in)) && (d->op != PBR_NORMAL_OP_ROTATE_BWD || plane_vec_ok(d->aux));
   dim3 grid, block;
   launch_shape(d->B, d->H, d->W, grid, block);
   normal_op_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(k);

@@ -443,8 +443,11 @@ class MaterialBase:
             cd = _channel_dim(normal)
             if normal.is_cuda and normal.dtype == torch.float32:
                 if torch.is_grad_enabled() and normal.requires_grad:
-                    raise RuntimeError("pypbr_b200: adjust_normal_strength scales the map in place and has no adjoint kernel; "
-                                       "detach the normal map first")
+                    # differentiable form (pbr_normal_op ROTATE_BWD): a new map, the source left as it is - autograd needs it
+                    from ..utils.functions import _RotateNormalsFn
+
+                    self._maps["normal"] = _RotateNormalsFn.apply(normal, float(strength_factor), 0.0)
+                    return self
                 from ..utils.functions import _normal_op
 
                 src = _cabi.rowmajor(normal.detach())

@@ -86,16 +86,16 @@ def rotate_normals(normal_map: torch.Tensor, angle: float) -> torch.Tensor:
     """
     Rotate the (x, y) part of every normal by `angle` degrees and renormalise (pypbr/utils/functions.py:69-108).
     Like the reference, the map is modified IN PLACE and returned.  (3,H,W) or (B,3,H,W).
+    A map that requires grad is NOT modified: the rotated map is returned as a new tensor with an adjoint kernel behind it
+    (pbr_normal_op ROTATE_BWD) - the reference's in-place assignment is tracked by autograd on a non-leaf tensor and refused
+    on a leaf; this form is differentiable for both.
     """
     _cabi.require_cuda(normal_map, "normal_map")
     if normal_map.dim() not in (3, 4) or normal_map.shape[-3] != 3:
         raise ValueError(f"normal_map must have shape (3, H, W) or (B, 3, H, W), got {tuple(normal_map.shape)}")
-    if torch.is_grad_enabled() and normal_map.requires_grad:
-        # the reference assigns into normal_map[0..2] in place (utils/functions.py:104-106), which autograd refuses on a
-        # leaf that requires grad; this kernel has no adjoint, so the call is refused for any such tensor instead of
-        # silently cutting the graph
-        raise RuntimeError("pypbr_b200: rotate_normals works in place and is not differentiable; pass normal_map.detach()")
     theta = math.radians(angle)
+    if torch.is_grad_enabled() and normal_map.requires_grad:
+        return _RotateNormalsFn.apply(normal_map, math.cos(theta), math.sin(theta))
     target = normal_map.detach()
     work = _cabi.rowmajor(target)
     _normal_op(work, work, _cabi.NORMAL_OP_ROTATE, cos_a=math.cos(theta), sin_a=math.sin(theta))
@@ -104,6 +104,27 @@ def rotate_normals(normal_map: torch.Tensor, angle: float) -> torch.Tensor:
     else:
         _cabi.touch(normal_map)
     return normal_map
+
+
+class _RotateNormalsFn(torch.autograd.Function):
+    """normalize(R(angle) (x, y), z) out of place, with its adjoint (pbr_normal_op ROTATE / ROTATE_BWD).  cos = strength,
+    sin = 0 is MaterialBase.adjust_normal_strength (base.py:689-706)."""
+
+    @staticmethod
+    def forward(ctx, normal_map, cos_a: float, sin_a: float):
+        src = _cabi.rowmajor(normal_map.detach())
+        ctx.save_for_backward(src)
+        ctx.args = (cos_a, sin_a)
+        out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+        return _normal_op(src, out, _cabi.NORMAL_OP_ROTATE, cos_a=cos_a, sin_a=sin_a)
+
+    @staticmethod
+    def backward(ctx, g):
+        (src,) = ctx.saved_tensors
+        cos_a, sin_a = ctx.args
+        d_in = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+        _normal_op(src, d_in, _cabi.NORMAL_OP_ROTATE_BWD, cos_a=cos_a, sin_a=sin_a, aux=_cabi.rowmajor(g.contiguous()))
+        return d_in, None, None
 
 
 def invert_normal(normals: torch.Tensor) -> torch.Tensor:
@@ -178,19 +199,53 @@ def compute_height_from_normal(normal_map: torch.Tensor, scale: float = 1.0,
     if convention not in (NormalConvention.OPENGL, NormalConvention.DIRECTX):
         raise ValueError("Unsupported normal convention.")
     _cabi.require_cuda(normal_map, "normal_map")
+    flip = 1 if convention == NormalConvention.DIRECTX else 0
     if torch.is_grad_enabled() and normal_map.requires_grad:
-        raise RuntimeError("pypbr_b200: compute_height_from_normal has no adjoint kernel; pass normal_map.detach()")
-    src = _cabi.rowmajor(normal_map.detach())
+        # differentiable like the reference's op sequence: the divergence kernel has an adjoint (DIVERGENCE_BWD), the solve and
+        # the [0, 1] normalisation below are torch ops autograd tracks
+        div = _DivergenceFn.apply(normal_map, float(scale), flip)
+        src = div
+    else:
+        src = _cabi.rowmajor(normal_map.detach())
+        div = _divergence(src, float(scale), flip)
     H, W = src.shape[-2:]
-    div = torch.empty((1, H, W), dtype=torch.float32, device=src.device)
-    _normal_op(src, div, _cabi.NORMAL_OP_DIVERGENCE, scale=float(scale), flip_y=1 if convention == NormalConvention.DIRECTX else 0)
     wy = 2 * math.pi * torch.arange(H, dtype=torch.float32, device=src.device).view(-1, 1) / H
     wx = 2 * math.pi * torch.arange(W, dtype=torch.float32, device=src.device).view(1, -1) / W
     eig = (2 * torch.cos(wx) - 2) + (2 * torch.cos(wy) - 2)
     eig[0, 0] = 1.0
     spec = torch.fft.fft2(div[0]) / eig
-    spec[0, 0] = 0
+    if spec.requires_grad:       # the same zero at the mean frequency, without writing into a tensor autograd holds
+        keep = torch.ones_like(eig)
+        keep[0, 0] = 0.0
+        spec = spec * keep
+    else:
+        spec[0, 0] = 0
     height = torch.fft.ifft2(spec).real
     height = height - height.mean()
     lo, hi = height.min(), height.max()
     return ((height - lo) / (hi - lo + 1e-8)).unsqueeze(0)
+
+
+def _divergence(src: torch.Tensor, scale: float, flip: int) -> torch.Tensor:
+    H, W = src.shape[-2:]
+    div = torch.empty((1, H, W), dtype=torch.float32, device=src.device)
+    return _normal_op(src, div, _cabi.NORMAL_OP_DIVERGENCE, scale=scale, flip_y=flip)
+
+
+class _DivergenceFn(torch.autograd.Function):
+    """The gradient field of a normal map and its divergence (utils/functions.py:241-283) with the adjoint kernel."""
+
+    @staticmethod
+    def forward(ctx, normal_map, scale: float, flip: int):
+        src = _cabi.rowmajor(normal_map.detach())
+        ctx.save_for_backward(src)
+        ctx.args = (scale, flip)
+        return _divergence(src, scale, flip)
+
+    @staticmethod
+    def backward(ctx, g):
+        (src,) = ctx.saved_tensors
+        scale, flip = ctx.args
+        d_n = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+        _normal_op(src, d_n, _cabi.NORMAL_OP_DIVERGENCE_BWD, scale=scale, flip_y=flip, aux=_cabi.rowmajor(g.contiguous()))
+        return d_n, None, None

@@ -537,8 +537,50 @@ def make_height_from_normal_fixture():
     print("height_normal_48x72: ok")
 
 
+def make_normal_ops_autograd_fixture():
+    """The reference's own autograd through rotate_normals (utils/functions.py:69-108; in place, hence run on a non-leaf),
+    MaterialBase.adjust_normal_strength (materials/base.py:689-706; in place as well) and compute_height_from_normal
+    (utils/functions.py:180-323), fp32 (the target) and fp64 (the arbiter)."""
+    from pypbr.utils import NormalConvention as RefConv
+    from pypbr.utils import compute_height_from_normal as ref_h_from_n
+    from pypbr.utils import rotate_normals as ref_rotate
+
+    gen = torch.Generator().manual_seed(707)
+    H, W = 20, 28
+    up = torch.tensor([0.0, 0.0, 1.0]).view(3, 1, 1)
+    n0 = torch.nn.functional.normalize(torch.randn(3, H, W, generator=gen) * 0.45 + up, dim=0)
+    w3 = torch.rand(3, H, W, generator=gen)
+    w1 = torch.rand(1, H, W, generator=gen)
+    arrs = {"normal": n0.numpy(), "w3": w3.numpy(), "w1": w1.numpy(), "angle": np.float32(37.0), "strength": np.float32(2.5),
+            "scale": np.float32(1.5)}
+    for dtype, tag in ((torch.float32, "32"), (torch.float64, "64")):
+        x = n0.detach().to(dtype).clone().requires_grad_(True)
+        y = ref_rotate(x * 1.0, 37.0)
+        (y * w3.to(dtype)).sum().backward()
+        arrs[f"rot_out{tag}"], arrs[f"rot_g{tag}"] = y.detach().numpy(), x.grad.numpy()
+
+        x = n0.detach().to(dtype).clone().requires_grad_(True)
+        m = BasecolorMetallicMaterial()
+        m._maps["normal"] = x * 1.0
+        m.adjust_normal_strength(2.5)
+        y = m._maps["normal"]
+        (y * w3.to(dtype)).sum().backward()
+        arrs[f"str_out{tag}"], arrs[f"str_g{tag}"] = y.detach().numpy(), x.grad.numpy()
+
+        for conv, ctag in ((RefConv.OPENGL, "gl"), (RefConv.DIRECTX, "dx")):
+            x = n0.detach().to(dtype).clone().requires_grad_(True)
+            h = ref_h_from_n(x, 1.5, conv)
+            (h * w1.to(dtype)).sum().backward()
+            arrs[f"hfn_out_{ctag}{tag}"], arrs[f"hfn_g_{ctag}{tag}"] = h.detach().numpy(), x.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "autograd_normal_ops.npz"), **arrs)
+    print("autograd_normal_ops: ok")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "normalops":   # only this fixture (the others are unchanged)
+        make_normal_ops_autograd_fixture()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "height":
         make_height_from_normal_fixture()
         sys.exit(0)
@@ -559,3 +601,4 @@ if __name__ == "__main__":
     make_geomgrad_cases()
     make_autograd_cases()
     make_height_from_normal_fixture()
+    make_normal_ops_autograd_fixture()

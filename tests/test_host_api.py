@@ -85,6 +85,15 @@ def test_argument_errors_come_back_as_codes_without_touching_the_gpu():
     assert lib.pbr_normal_op(ctypes.byref(n), None) == -1
     n.in_ = n.out = _cabi.PbrPlane(fake, 0, 16, 4)
     assert lib.pbr_normal_op(ctypes.byref(n), None) == -1    # a stencil cannot run in place
+    for op in (_cabi.NORMAL_OP_FROM_HEIGHT_BWD, _cabi.NORMAL_OP_ROTATE_BWD, _cabi.NORMAL_OP_DIVERGENCE_BWD):
+        n.op = op
+        n.in_, n.out = _cabi.PbrPlane(fake, 0, 16, 4), _cabi.PbrPlane(fake + 4096, 0, 16, 4)
+        n.aux = _cabi.PbrPlane(None, 0, 0, 0)
+        assert lib.pbr_normal_op(ctypes.byref(n), None) == -1    # an adjoint needs the incoming gradient
+        n.aux = n.out
+        assert lib.pbr_normal_op(ctypes.byref(n), None) == -1    # ... and cannot write over it
+    n.op = _cabi.NORMAL_OP_DIVERGENCE_BWD + 1
+    assert lib.pbr_normal_op(ctypes.byref(n), None) == -3
 
 
 # ------------------------------------------------------------------ material container
