@@ -116,7 +116,7 @@ struct GeomCache {
 
 template <class V>
 PBR_HD V p5_from_half(V hx, V hy, V hz, float vx, float vy, float vz) {
-  V c = clamp01(xdot3(hx, hy, hz, splat<V>(vx), splat<V>(vy), splat<V>(vz)));
+  V c = xdot3_sat(hx, hy, hz, splat<V>(vx), splat<V>(vy), splat<V>(vz));
   V omc = 1.0f - c;
   V o2 = omc * omc;
   return o2 * o2 * omc;
@@ -219,7 +219,7 @@ PBR_HD void ct_forward_group(const CtStage& S, const CtFlags& F, const V (&araw)
       light_geom<kLight, V, N>(S, l, x, y, hoisted, i, gc, g);
       LightFwd<V> f;
       V col[3];
-      shade_light_fwd<kWorkflow>(t[i], g, S.light[l].inten, f, col);
+      shade_light_fwd<kWorkflow, false>(t[i], g, S.light[l].inten, f, col);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         if (F.per_light) outv[c][i] = encode_out(col[c], F.return_srgb);
@@ -354,7 +354,7 @@ PBR_HD void ct_backward_group(const CtStage& S, const CtFlags& F, const V (&araw
           light_geom<kLight, V, N>(S, l, x, y, hoisted, i, gc, g);
           LightFwd<V> f;
           V col[3];
-          shade_light_fwd<kWorkflow>(t[i], g, S.light[l].inten, f, col);
+          shade_light_fwd<kWorkflow, false>(t[i], g, S.light[l].inten, f, col);
 #pragma unroll
           for (int c = 0; c < 3; ++c) acc[c][i] = xadd(acc[c][i], col[c]);
         }
